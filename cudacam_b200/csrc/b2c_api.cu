@@ -1,0 +1,856 @@
+// b2c_api.cu -- the C ABI of libb200canny.so (see include/b200canny.h) and the host driver behind it.
+//
+// Replaces the host class of the reference, cvp::cuda::CannyEdge (src/cvp/cannyEdgeH.{hpp,cu}):
+//   ctor/_initAlloc (:16-38,:340-385)  -> b2c_create          (device buffers, pinned staging, streams)
+//   run            (:49-120)           -> b2c_run             (one host frame, blocking, stage select)
+//   _loadInputImage(:122-152)          -> async pitched H2D copy on the handle's stream
+//   _run* x6 + CPU hysteresis loop (:214-338) -> 1 fused stencil launch + 1 cooperative hysteresis launch
+//   _sendOutputToOpenGL (:154-212)     -> the VIEW buffer (tight w*h bytes, what the PBO receives)
+//   _start/_endCudaTimer (:409-430)    -> event pairs read back only by b2c_last_timings
+//   checkCudaErrors -> exit (helper.hpp:4-17) -> status codes, never exit
+// plus what the reference does not have: device-resident batches, a pinned double-buffered host
+// pipeline, and row-band mode for one image split over several GPUs.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/b200canny.h"
+#include "b2c_device.cuh"
+#include "k_hysteresis.cuh"
+#include "k_stencil_fused.cuh"
+#include "k_stencil_tile.cuh"
+#include "k_views.cuh"
+
+namespace
+{
+constexpr int NSLOT = 2;   // ping-pong halves of the batch buffers in the host pipeline
+
+struct Ev {
+  cudaEvent_t e = nullptr;
+};
+
+}// namespace
+
+struct b2c_ctx {
+  int dev = 0, w = 0, h = 0, ch = 3, max_batch = 1;
+  int sm_count = 0;
+  uint8_t lo = 10, hi = 40;   // src/cvp/cannyEdgeH.cu:22-23
+  bool profiling = true;      // src/cvp/cannyEdgeH.cu:24
+  int stencil_impl = 0;       // 0 fused, 1 tile
+  int hyst_tile_rows = 16;
+  int hyst_max_rounds = 1 << 20;
+
+  // geometry
+  int map_pitch = 0;      // u32 per row of the 2-bit map
+  int wpr = 0;            // u32 per row of a bit plane (used words)
+  int plane_pitch = 0;    // u32 per row of a bit plane (allocated)
+  int rows_alloc = 0;     // rows per frame of map / planes / edges (h, or band rows)
+  size_t in_row_stride = 0, in_frame_stride = 0;   // own input buffer
+  size_t edges_pitch = 0, edges_frame_stride = 0;
+  int pitch8 = 0, pitchf = 0;   // stage buffers, elements
+
+  // device memory
+  uint8_t *d_in = nullptr;
+  uint32_t *d_map2 = nullptr;
+  uint32_t *d_S_base = nullptr, *d_C_base = nullptr;   // incl. ghost rows
+  uint8_t *d_edges = nullptr;
+  uint8_t *d_mono = nullptr, *d_blur = nullptr, *d_nms = nullptr, *d_thresh = nullptr, *d_view = nullptr;
+  float *d_grad = nullptr;
+  int *d_flags = nullptr;
+  int *h_flags = nullptr;   // pinned mirror
+
+  // last input (for on-demand stage buffers)
+  const uint8_t *last_in = nullptr;
+  size_t last_row_stride = 0;
+  bool have_frame = false, stages_valid = false;
+  int last_stage = -1;
+
+  // host pipeline
+  uint8_t *h_in[NSLOT] = { nullptr, nullptr };
+  uint8_t *h_out[NSLOT] = { nullptr, nullptr };
+  size_t h_in_bytes = 0, h_out_bytes = 0;
+  cudaStream_t s_main = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_in[NSLOT] = {}, ev_k[NSLOT] = {}, ev_out[NSLOT] = {};
+  cudaEvent_t ev_t[5] = {};   // timing marks: start, after upload, after stencil, after hysteresis, end
+  bool timings_valid = false;
+
+  // band mode
+  bool band = false;
+  int band_y0 = 0, h_glob = 0;
+
+  int hyst_grid = 0, hyst_smem = 0;
+  long long launches = 0;
+  std::string last_err;
+};
+
+namespace
+{
+int set_err(b2c_ctx *c, cudaError_t e, const char *what)
+{
+  if (c) {
+    c->last_err = what;
+    c->last_err += ": ";
+    c->last_err += cudaGetErrorString(e);
+  }
+  (void)cudaGetLastError();
+  return B2C_ERR_CUDA;
+}
+#define CK(c, x)                                      \
+  do {                                                \
+    cudaError_t e_ = (x);                             \
+    if (e_ != cudaSuccess) return set_err(c, e_, #x); \
+  } while (0)
+
+inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+void fill_gk(float gk[25])
+{
+  // src/cvp/cannyEdgeH.cu:372-379: k * (1/159.0f), single fp32 rounding of the product, on the host
+  static const float k[25] = { 2, 4, 5, 4, 2, 4, 9, 12, 9, 4, 5, 12, 15, 12, 5, 4, 9, 12, 9, 4, 2, 4, 5, 4, 2 };
+  const float inv = 1 / 159.0f;
+  for (int i = 0; i < 25; ++i) {
+    volatile float v = k[i] * inv;
+    gk[i] = v;
+  }
+}
+
+uint32_t *S0(b2c_ctx *c) { return c->d_S_base + c->plane_pitch; }
+uint32_t *C0(b2c_ctx *c) { return c->d_C_base + c->plane_pitch; }
+long long plane_frame_stride(const b2c_ctx *c) { return (long long)(c->rows_alloc + 2) * c->plane_pitch; }
+
+int alloc_common(b2c_ctx *c)
+{
+  const int w = c->w, rows = c->rows_alloc, nb = c->max_batch;
+  c->map_pitch = (w + 15) / 16;
+  c->wpr = (w + 31) / 32;
+  c->plane_pitch = (int)round_up((size_t)c->wpr, 4);
+  c->edges_pitch = (size_t)w;   // tight, like the reference's PBO (src/imgui/imguiApp.cpp:76)
+  c->edges_frame_stride = round_up(c->edges_pitch * rows, 256);
+  c->pitch8 = (int)round_up((size_t)w, 16);
+  c->pitchf = (int)round_up((size_t)w, 4);
+  cudaDeviceProp prop;
+  CK(c, cudaGetDeviceProperties(&prop, c->dev));
+  c->sm_count = prop.multiProcessorCount;
+  if (!prop.cooperativeLaunch) {
+    c->last_err = "device does not support cooperative launch";
+    return B2C_ERR_UNSUPPORTED;
+  }
+  CK(c, cudaMalloc(&c->d_map2, (size_t)nb * rows * c->map_pitch * 4));
+  const size_t plane_bytes = (size_t)nb * plane_frame_stride(c) * 4;
+  CK(c, cudaMalloc(&c->d_S_base, plane_bytes));
+  CK(c, cudaMalloc(&c->d_C_base, plane_bytes));
+  CK(c, cudaMemset(c->d_S_base, 0, plane_bytes));
+  CK(c, cudaMemset(c->d_C_base, 0, plane_bytes));
+  CK(c, cudaMalloc(&c->d_edges, (size_t)nb * c->edges_frame_stride));
+  CK(c, cudaMalloc(&c->d_flags, 16 * sizeof(int)));
+  CK(c, cudaMemset(c->d_flags, 0, 16 * sizeof(int)));
+  CK(c, cudaMallocHost(&c->h_flags, 16 * sizeof(int)));
+  memset(c->h_flags, 0, 16 * sizeof(int));
+  CK(c, cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking));
+  CK(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+  CK(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+  for (int i = 0; i < NSLOT; ++i) {
+    CK(c, cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+    CK(c, cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
+    CK(c, cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+  }
+  for (auto &e : c->ev_t) CK(c, cudaEventCreate(&e));
+
+  // hysteresis launch geometry: persistent cooperative grid, as many CTAs as fit
+  c->hyst_smem = b2c::hyst_smem_bytes(c->hyst_tile_rows);
+  CK(c, cudaFuncSetAttribute(b2c::k_hysteresis, cudaFuncAttributeMaxDynamicSharedMemorySize, c->hyst_smem));
+  int per_sm = 0;
+  CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b2c::k_hysteresis, b2c::HYST_THREADS, c->hyst_smem));
+  if (per_sm < 1) {
+    c->last_err = "hysteresis kernel does not fit on an SM";
+    return B2C_ERR_CUDA;
+  }
+  c->hyst_grid = c->sm_count * std::min(per_sm, 4);
+  CK(c, cudaFuncSetAttribute(b2c::k_stencil_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2c::TILE_SMEM));
+  CK(c, cudaFuncSetAttribute(b2c::k_stencil_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2c::TILE_SMEM));
+  return b2c::fused_configure() == cudaSuccess ? B2C_OK : set_err(c, cudaGetLastError(), "fused_configure");
+}
+
+void fill_stencil_params(b2c_ctx *c, B2cStencilParams &p, const uint8_t *bgr, size_t row_stride, size_t frame_stride, int n)
+{
+  memset(&p, 0, sizeof(p));
+  p.bgr = bgr;
+  p.row_stride = (long long)row_stride;
+  p.frame_stride = (long long)frame_stride;
+  p.w = c->w;
+  p.h = c->rows_alloc;
+  p.y0 = c->band ? c->band_y0 : 0;
+  p.h_glob = c->band ? c->h_glob : c->h;
+  p.nframes = n;
+  p.map2 = c->d_map2;
+  p.map_pitch = c->map_pitch;
+  p.map_frame_stride = (long long)c->rows_alloc * c->map_pitch;
+  p.lo = c->lo;
+  p.hi = c->hi;
+  fill_gk(p.gk);
+  p.pitch8 = c->pitch8;
+  p.pitchf = c->pitchf;
+}
+
+// Fused stencil: BGR8 -> 2-bit map for n frames.
+int launch_stencil(b2c_ctx *c, const uint8_t *bgr, size_t row_stride, size_t frame_stride, int n, cudaStream_t st)
+{
+  B2cStencilParams p;
+  fill_stencil_params(c, p, bgr, row_stride, frame_stride, n);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(bgr) | row_stride | frame_stride) & 15) == 0;
+  if (c->stencil_impl == 0 && aligned && b2c::fused_supported(p)) {
+    cudaError_t e = b2c::fused_launch(p, c->sm_count, st);
+    if (e != cudaSuccess) return set_err(c, e, "k_stencil_fused launch");
+  } else {
+    dim3 grid((c->w + b2c::TILE_W - 1) / b2c::TILE_W, (c->rows_alloc + b2c::TILE_H - 1) / b2c::TILE_H, n);
+    b2c::k_stencil_tile<false><<<grid, b2c::TILE_THREADS, b2c::TILE_SMEM, st>>>(p);
+    CK(c, cudaGetLastError());
+  }
+  c->launches++;
+  return B2C_OK;
+}
+
+// All-stages variant for frame 0 (mono, blur, grad, nms, thresh buffers of the reference).
+int launch_stencil_emit(b2c_ctx *c, const uint8_t *bgr, size_t row_stride, cudaStream_t st)
+{
+  if (!c->d_mono) {
+    const size_t n8 = (size_t)c->pitch8 * c->rows_alloc;
+    CK(c, cudaMalloc(&c->d_mono, n8));
+    CK(c, cudaMalloc(&c->d_blur, n8));
+    CK(c, cudaMalloc(&c->d_nms, n8));
+    CK(c, cudaMalloc(&c->d_thresh, n8));
+    CK(c, cudaMalloc(&c->d_grad, (size_t)c->pitchf * c->rows_alloc * 4));
+    CK(c, cudaMalloc(&c->d_view, (size_t)c->w * c->rows_alloc));
+  }
+  B2cStencilParams p;
+  fill_stencil_params(c, p, bgr, row_stride, 0, 1);
+  p.mono = c->d_mono;
+  p.blur = c->d_blur;
+  p.nms = c->d_nms;
+  p.thresh = c->d_thresh;
+  p.grad = c->d_grad;
+  dim3 grid((c->w + b2c::TILE_W - 1) / b2c::TILE_W, (c->rows_alloc + b2c::TILE_H - 1) / b2c::TILE_H, 1);
+  b2c::k_stencil_tile<true><<<grid, b2c::TILE_THREADS, b2c::TILE_SMEM, st>>>(p);
+  CK(c, cudaGetLastError());
+  c->launches++;
+  c->stages_valid = true;
+  return B2C_OK;
+}
+
+int launch_hysteresis(b2c_ctx *c, int n, uint8_t *edges, size_t edges_pitch, size_t edges_frame_stride, int skip_init, int skip_expand, cudaStream_t st)
+{
+  B2cHystParams p;
+  memset(&p, 0, sizeof(p));
+  p.map2 = c->d_map2;
+  p.map_pitch = c->map_pitch;
+  p.map_frame_stride = (long long)c->rows_alloc * c->map_pitch;
+  p.S = S0(c);
+  p.C = C0(c);
+  p.plane_pitch = c->plane_pitch;
+  p.plane_frame_stride = plane_frame_stride(c);
+  p.w = c->w;
+  p.h = c->rows_alloc;
+  p.nframes = n;
+  p.edges = edges;
+  p.edges_pitch = (long long)edges_pitch;
+  p.edges_frame_stride = (long long)edges_frame_stride;
+  p.flags = c->d_flags;
+  p.max_rounds = c->hyst_max_rounds;
+  p.tile_rows = c->hyst_tile_rows;
+  p.skip_init = skip_init;
+  p.skip_expand = skip_expand;
+  void *args[] = { &p };
+  CK(c, cudaLaunchCooperativeKernel((const void *)b2c::k_hysteresis, dim3(c->hyst_grid), dim3(b2c::HYST_THREADS), args, (size_t)c->hyst_smem, st));
+  c->launches++;
+  return B2C_OK;
+}
+
+int check_handle(b2c_ctx *c) { return c ? B2C_OK : B2C_ERR_INVALID; }
+
+struct DevGuard {
+  int prev = -1;
+  explicit DevGuard(int dev)
+  {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DevGuard()
+  {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+}// namespace
+
+extern "C" {
+
+int b2c_create(b2c_handle *out, int device, int width, int height, int channels, int max_batch)
+{
+  if (!out || width < 1 || height < 1 || max_batch < 1) return B2C_ERR_INVALID;
+  *out = nullptr;
+  if (channels != 3) return B2C_ERR_UNSUPPORTED;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    (void)cudaGetLastError();
+    return B2C_ERR_CUDA;
+  }
+  b2c_ctx *c = new (std::nothrow) b2c_ctx;
+  if (!c) return B2C_ERR_NOMEM;
+  c->dev = device;
+  c->w = width;
+  c->h = height;
+  c->ch = channels;
+  c->max_batch = max_batch;
+  c->rows_alloc = height;
+  DevGuard g(device);
+  c->in_row_stride = round_up((size_t)width * 3, 16);
+  c->in_frame_stride = c->in_row_stride * height;
+  int rc = alloc_common(c);
+  if (rc == B2C_OK && cudaMalloc(&c->d_in, (size_t)max_batch * c->in_frame_stride) != cudaSuccess) rc = set_err(c, cudaGetLastError(), "cudaMalloc(d_in)");
+  if (rc != B2C_OK) {
+    fprintf(stderr, "[b200canny] b2c_create failed: %s\n", c->last_err.c_str());
+    b2c_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return B2C_OK;
+}
+
+int b2c_create_band(b2c_handle *out, int device, int width, int band_rows, int y0, int height_global)
+{
+  if (!out || width < 1 || band_rows < 1 || y0 < 0 || y0 + band_rows > height_global) return B2C_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    (void)cudaGetLastError();
+    return B2C_ERR_CUDA;
+  }
+  b2c_ctx *c = new (std::nothrow) b2c_ctx;
+  if (!c) return B2C_ERR_NOMEM;
+  c->dev = device;
+  c->w = width;
+  c->h = band_rows;
+  c->max_batch = 1;
+  c->rows_alloc = band_rows;
+  c->band = true;
+  c->band_y0 = y0;
+  c->h_glob = height_global;
+  DevGuard g(device);
+  int rc = alloc_common(c);
+  if (rc != B2C_OK) {
+    fprintf(stderr, "[b200canny] b2c_create_band failed: %s\n", c->last_err.c_str());
+    b2c_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return B2C_OK;
+}
+
+void b2c_destroy(b2c_handle c)
+{
+  if (!c) return;
+  DevGuard g(c->dev);
+  if (c->s_main) cudaStreamSynchronize(c->s_main);
+  if (c->s_h2d) cudaStreamSynchronize(c->s_h2d);
+  if (c->s_d2h) cudaStreamSynchronize(c->s_d2h);
+  cudaFree(c->d_in);
+  cudaFree(c->d_map2);
+  cudaFree(c->d_S_base);
+  cudaFree(c->d_C_base);
+  cudaFree(c->d_edges);
+  cudaFree(c->d_mono);
+  cudaFree(c->d_blur);
+  cudaFree(c->d_nms);
+  cudaFree(c->d_thresh);
+  cudaFree(c->d_view);
+  cudaFree(c->d_grad);
+  cudaFree(c->d_flags);
+  if (c->h_flags) cudaFreeHost(c->h_flags);
+  for (int i = 0; i < NSLOT; ++i) {
+    if (c->h_in[i]) cudaFreeHost(c->h_in[i]);
+    if (c->h_out[i]) cudaFreeHost(c->h_out[i]);
+    if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+    if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
+    if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+  }
+  for (auto &e : c->ev_t)
+    if (e) cudaEventDestroy(e);
+  if (c->s_main) cudaStreamDestroy(c->s_main);
+  if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+  if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+  (void)cudaGetLastError();
+  delete c;
+}
+
+// src/cvp/cannyEdgeH.hpp:25-29
+int b2c_set_low_threshold(b2c_handle c, uint8_t low)
+{
+  if (!c) return B2C_ERR_INVALID;
+  c->lo = std::min(low, c->hi);
+  c->stages_valid = false;
+  return B2C_OK;
+}
+int b2c_set_high_threshold(b2c_handle c, uint8_t high)
+{
+  if (!c) return B2C_ERR_INVALID;
+  c->hi = std::max(high, c->lo);
+  c->stages_valid = false;
+  return B2C_OK;
+}
+int b2c_get_low_threshold(b2c_handle c) { return c ? c->lo : B2C_ERR_INVALID; }
+int b2c_get_high_threshold(b2c_handle c) { return c ? c->hi : B2C_ERR_INVALID; }
+
+int b2c_enable_profiling(b2c_handle c, int on)
+{
+  if (!c) return B2C_ERR_INVALID;
+  c->profiling = on != 0;
+  return B2C_OK;
+}
+int b2c_is_profiling_enabled(b2c_handle c) { return c ? (c->profiling ? 1 : 0) : B2C_ERR_INVALID; }
+
+int b2c_last_timings(b2c_handle c, float *ms, int n)
+{
+  if (!c || !ms || n < 1) return B2C_ERR_INVALID;
+  if (!c->timings_valid) return B2C_ERR_STATE;
+  DevGuard g(c->dev);
+  float v[6] = { 0, 0, 0, 0, 0, 0 };
+  CK(c, cudaEventSynchronize(c->ev_t[4]));
+  for (int i = 0; i < 4; ++i) CK(c, cudaEventElapsedTime(&v[i], c->ev_t[i], c->ev_t[i + 1]));
+  CK(c, cudaEventElapsedTime(&v[4], c->ev_t[0], c->ev_t[4]));
+  v[5] = (float)c->h_flags[3];
+  for (int i = 0; i < n && i < 6; ++i) ms[i] = v[i];
+  return B2C_OK;
+}
+
+int b2c_run(b2c_handle c, const uint8_t *host_bgr, size_t row_stride, int final_stage)
+{
+  if (!c || !host_bgr || c->band) return B2C_ERR_INVALID;
+  if (final_stage < B2C_STAGE_MONO || final_stage > B2C_STAGE_HYSTER) return B2C_ERR_INVALID;
+  if (row_stride < (size_t)c->w * 3) return B2C_ERR_SIZE;
+  DevGuard g(c->dev);
+  cudaStream_t st = c->s_main;
+  const bool prof = c->profiling;
+  if (prof) CK(c, cudaEventRecord(c->ev_t[0], st));
+  CK(c, cudaMemcpy2DAsync(c->d_in, c->in_row_stride, host_bgr, row_stride, (size_t)c->w * 3, c->h, cudaMemcpyHostToDevice, st));
+  if (prof) CK(c, cudaEventRecord(c->ev_t[1], st));
+  c->last_in = c->d_in;
+  c->last_row_stride = c->in_row_stride;
+  c->have_frame = true;
+  c->stages_valid = false;
+  c->last_stage = final_stage;
+  int rc;
+  if (final_stage == B2C_STAGE_HYSTER) {
+    if ((rc = launch_stencil(c, c->d_in, c->in_row_stride, c->in_frame_stride, 1, st)) != B2C_OK) return rc;
+    if (prof) CK(c, cudaEventRecord(c->ev_t[2], st));
+    if ((rc = launch_hysteresis(c, 1, c->d_edges, c->edges_pitch, c->edges_frame_stride, 0, 0, st)) != B2C_OK) return rc;
+    if (prof) CK(c, cudaEventRecord(c->ev_t[3], st));
+  } else {
+    // stage views: the pipeline stops after the selected stage (src/cvp/cannyEdgeH.cu:58-115)
+    if ((rc = launch_stencil_emit(c, c->d_in, c->in_row_stride, st)) != B2C_OK) return rc;
+    if (prof) CK(c, cudaEventRecord(c->ev_t[2], st));
+    if (prof) CK(c, cudaEventRecord(c->ev_t[3], st));
+    const int blocks = c->sm_count * 4;
+    if (final_stage == B2C_STAGE_GRADIENT) {
+      b2c::k_grad_view<<<blocks, 256, 0, st>>>(c->d_grad, c->pitchf, c->d_view, c->w, c->w, c->h);
+    } else {
+      const uint8_t *src = final_stage == B2C_STAGE_MONO ? c->d_mono : final_stage == B2C_STAGE_GAUSSIAN ? c->d_blur : final_stage == B2C_STAGE_NMS ? c->d_nms : c->d_thresh;
+      b2c::k_copy2d_u8<<<blocks, 256, 0, st>>>(src, c->pitch8, c->d_view, c->w, c->w, c->h);
+    }
+    CK(c, cudaGetLastError());
+    c->launches++;
+  }
+  CK(c, cudaMemcpyAsync(c->h_flags, c->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (prof) CK(c, cudaEventRecord(c->ev_t[4], st));
+  CK(c, cudaStreamSynchronize(st));   // blocking, like the reference's run()
+  c->timings_valid = prof;
+  return B2C_OK;
+}
+
+int b2c_run_device(b2c_handle c, const uint8_t *dev_bgr, size_t row_stride, size_t frame_stride, int n, uint8_t *dev_edges, size_t edges_pitch, size_t edges_frame_stride, void *stream)
+{
+  if (!c || !dev_bgr || c->band || n < 1 || n > c->max_batch) return B2C_ERR_INVALID;
+  if (row_stride < (size_t)c->w * 3) return B2C_ERR_SIZE;
+  DevGuard g(c->dev);
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->s_main;
+  if (!dev_edges) {
+    dev_edges = c->d_edges;
+    edges_pitch = c->edges_pitch;
+    edges_frame_stride = c->edges_frame_stride;
+  } else if (edges_pitch < (size_t)c->w) {
+    return B2C_ERR_SIZE;
+  }
+  const bool prof = c->profiling;
+  if (prof) {
+    CK(c, cudaEventRecord(c->ev_t[0], st));
+    CK(c, cudaEventRecord(c->ev_t[1], st));
+  }
+  int rc;
+  if ((rc = launch_stencil(c, dev_bgr, row_stride, frame_stride, n, st)) != B2C_OK) return rc;
+  if (prof) CK(c, cudaEventRecord(c->ev_t[2], st));
+  if ((rc = launch_hysteresis(c, n, dev_edges, edges_pitch, edges_frame_stride, 0, 0, st)) != B2C_OK) return rc;
+  if (prof) {
+    CK(c, cudaEventRecord(c->ev_t[3], st));
+    CK(c, cudaEventRecord(c->ev_t[4], st));
+  }
+  c->last_in = dev_bgr;
+  c->last_row_stride = row_stride;
+  c->have_frame = true;
+  c->stages_valid = false;
+  c->last_stage = B2C_STAGE_HYSTER;
+  c->timings_valid = prof;
+  return B2C_OK;
+}
+
+int b2c_stencil_device(b2c_handle c, const uint8_t *dev_bgr, size_t row_stride, size_t frame_stride, int n, void *stream)
+{
+  if (!c || !dev_bgr || c->band || n < 1 || n > c->max_batch) return B2C_ERR_INVALID;
+  if (row_stride < (size_t)c->w * 3) return B2C_ERR_SIZE;
+  DevGuard g(c->dev);
+  return launch_stencil(c, dev_bgr, row_stride, frame_stride, n, stream ? (cudaStream_t)stream : c->s_main);
+}
+
+int b2c_hysteresis_device(b2c_handle c, int n, uint8_t *dev_edges, size_t edges_pitch, size_t edges_frame_stride, void *stream)
+{
+  if (!c || c->band || n < 1 || n > c->max_batch) return B2C_ERR_INVALID;
+  DevGuard g(c->dev);
+  if (!dev_edges) {
+    dev_edges = c->d_edges;
+    edges_pitch = c->edges_pitch;
+    edges_frame_stride = c->edges_frame_stride;
+  }
+  return launch_hysteresis(c, n, dev_edges, edges_pitch, edges_frame_stride, 0, 0, stream ? (cudaStream_t)stream : c->s_main);
+}
+
+int b2c_run_batch_host(b2c_handle c, const uint8_t *frames, size_t row_stride, int n, uint8_t *edges_out, int packed_bits)
+{
+  if (!c || !frames || !edges_out || c->band || n < 1) return B2C_ERR_INVALID;
+  if (row_stride < (size_t)c->w * 3) return B2C_ERR_SIZE;
+  DevGuard g(c->dev);
+  const int w = c->w, h = c->h;
+  const int slot_frames = std::max(1, c->max_batch / NSLOT);
+  const int nslots = c->max_batch >= NSLOT ? NSLOT : 1;
+  const size_t in_frame_host = row_stride * h;
+  const size_t out_row = packed_bits ? (size_t)c->wpr * 4 : (size_t)w;
+  const size_t out_frame_host = out_row * h;
+
+  // Is the caller's memory pinned?  If not, stage through our own pinned ring.
+  cudaPointerAttributes ai, ao;
+  const bool in_pinned = cudaPointerGetAttributes(&ai, frames) == cudaSuccess && ai.type == cudaMemoryTypeHost;
+  const bool out_pinned = cudaPointerGetAttributes(&ao, edges_out) == cudaSuccess && ao.type == cudaMemoryTypeHost;
+  (void)cudaGetLastError();
+  if (!in_pinned && c->h_in_bytes < (size_t)slot_frames * in_frame_host) {
+    for (int s = 0; s < nslots; ++s) {
+      if (c->h_in[s]) cudaFreeHost(c->h_in[s]);
+      c->h_in[s] = nullptr;
+      CK(c, cudaMallocHost(&c->h_in[s], (size_t)slot_frames * in_frame_host));
+    }
+    c->h_in_bytes = (size_t)slot_frames * in_frame_host;
+  }
+  if (!out_pinned && c->h_out_bytes < (size_t)slot_frames * out_frame_host) {
+    for (int s = 0; s < nslots; ++s) {
+      if (c->h_out[s]) cudaFreeHost(c->h_out[s]);
+      c->h_out[s] = nullptr;
+      CK(c, cudaMallocHost(&c->h_out[s], (size_t)slot_frames * out_frame_host));
+    }
+    c->h_out_bytes = (size_t)slot_frames * out_frame_host;
+  }
+
+  const int nchunks = (n + slot_frames - 1) / slot_frames;
+  int pending_out[NSLOT] = { -1, -1 };   // chunk whose D2H into h_out[slot] still has to be copied out
+  auto drain = [&](int slot) -> int {
+    const int k = pending_out[slot];
+    if (k < 0) return B2C_OK;
+    CK(c, cudaEventSynchronize(c->ev_out[slot]));
+    if (!out_pinned) {
+      const int f0 = k * slot_frames, cnt = std::min(slot_frames, n - f0);
+      memcpy(edges_out + (size_t)f0 * out_frame_host, c->h_out[slot], (size_t)cnt * out_frame_host);
+    }
+    pending_out[slot] = -1;
+    return B2C_OK;
+  };
+
+  for (int k = 0; k < nchunks; ++k) {
+    const int slot = k % nslots;
+    const int f0 = k * slot_frames, cnt = std::min(slot_frames, n - f0);
+    int rc = drain(slot);   // also guarantees the slot's device halves and pinned buffers are free
+    if (rc != B2C_OK) return rc;
+    if (k >= nslots) CK(c, cudaStreamWaitEvent(c->s_h2d, c->ev_k[slot], 0));   // input half still being read by chunk k-nslots
+    uint8_t *din = c->d_in + (size_t)slot * slot_frames * c->in_frame_stride;
+    const uint8_t *src = frames + (size_t)f0 * in_frame_host;
+    if (!in_pinned) {
+      memcpy(c->h_in[slot], src, (size_t)cnt * in_frame_host);
+      src = c->h_in[slot];
+    }
+    if (row_stride == c->in_row_stride) {
+      CK(c, cudaMemcpyAsync(din, src, (size_t)cnt * in_frame_host, cudaMemcpyHostToDevice, c->s_h2d));
+    } else {
+      for (int f = 0; f < cnt; ++f)
+        CK(c, cudaMemcpy2DAsync(din + (size_t)f * c->in_frame_stride, c->in_row_stride, src + (size_t)f * in_frame_host, row_stride, (size_t)w * 3, h, cudaMemcpyHostToDevice, c->s_h2d));
+    }
+    CK(c, cudaEventRecord(c->ev_in[slot], c->s_h2d));
+
+    CK(c, cudaStreamWaitEvent(c->s_main, c->ev_in[slot], 0));
+    if ((rc = launch_stencil(c, din, c->in_row_stride, c->in_frame_stride, cnt, c->s_main)) != B2C_OK) return rc;
+    uint8_t *dedges = c->d_edges + (size_t)slot * slot_frames * c->edges_frame_stride;
+    // all slots share the map / plane buffers: the compute stream serialises them
+    if ((rc = launch_hysteresis(c, cnt, dedges, c->edges_pitch, c->edges_frame_stride, 0, packed_bits ? 1 : 0, c->s_main)) != B2C_OK) return rc;
+    uint8_t *hout = out_pinned ? edges_out + (size_t)f0 * out_frame_host : c->h_out[slot];
+    if (packed_bits) {
+      // the S planes are shared between slots, so the D2H of the bit planes stays on the compute stream
+      for (int f = 0; f < cnt; ++f)
+        CK(c, cudaMemcpy2DAsync(hout + (size_t)f * out_frame_host, out_row, S0(c) + (size_t)f * plane_frame_stride(c), (size_t)c->plane_pitch * 4, out_row, h, cudaMemcpyDeviceToHost, c->s_main));
+      CK(c, cudaEventRecord(c->ev_k[slot], c->s_main));
+      CK(c, cudaEventRecord(c->ev_out[slot], c->s_main));
+    } else {
+      CK(c, cudaEventRecord(c->ev_k[slot], c->s_main));
+      CK(c, cudaStreamWaitEvent(c->s_d2h, c->ev_k[slot], 0));
+      if (c->edges_frame_stride == out_frame_host) {
+        CK(c, cudaMemcpyAsync(hout, dedges, (size_t)cnt * out_frame_host, cudaMemcpyDeviceToHost, c->s_d2h));
+      } else {
+        for (int f = 0; f < cnt; ++f)
+          CK(c, cudaMemcpyAsync(hout + (size_t)f * out_frame_host, dedges + (size_t)f * c->edges_frame_stride, out_frame_host, cudaMemcpyDeviceToHost, c->s_d2h));
+      }
+      CK(c, cudaEventRecord(c->ev_out[slot], c->s_d2h));
+      // the next chunk that reuses this slot's edge half must wait for this D2H
+      CK(c, cudaStreamWaitEvent(c->s_main, c->ev_out[slot], 0));
+    }
+    pending_out[slot] = k;
+  }
+  for (int s = 0; s < nslots; ++s) {
+    int rc = drain(s);
+    if (rc != B2C_OK) return rc;
+  }
+  CK(c, cudaStreamSynchronize(c->s_main));
+  c->last_in = c->d_in + (size_t)((nchunks - 1) % nslots) * slot_frames * c->in_frame_stride;
+  c->last_row_stride = c->in_row_stride;
+  c->have_frame = true;
+  c->stages_valid = false;
+  c->last_stage = B2C_STAGE_HYSTER;
+  c->timings_valid = false;
+  return B2C_OK;
+}
+
+int b2c_get_buffer(b2c_handle c, int id, const void **dev_ptr, size_t *pitch_bytes, int *elem_size)
+{
+  if (!c || !dev_ptr) return B2C_ERR_INVALID;
+  if (!c->have_frame) return B2C_ERR_STATE;
+  DevGuard g(c->dev);
+  const void *p = nullptr;
+  size_t pitch = 0;
+  int es = 1;
+  if (id >= B2C_BUF_MONO && id <= B2C_BUF_THRESH) {
+    if (c->band) return B2C_ERR_UNSUPPORTED;
+    if (!c->stages_valid) {
+      int rc = launch_stencil_emit(c, c->last_in, c->last_row_stride, c->s_main);
+      if (rc != B2C_OK) return rc;
+      CK(c, cudaStreamSynchronize(c->s_main));
+    }
+    switch (id) {
+    case B2C_BUF_MONO: p = c->d_mono; pitch = c->pitch8; break;
+    case B2C_BUF_BLUR: p = c->d_blur; pitch = c->pitch8; break;
+    case B2C_BUF_NMS: p = c->d_nms; pitch = c->pitch8; break;
+    case B2C_BUF_THRESH: p = c->d_thresh; pitch = c->pitch8; break;
+    default: p = c->d_grad; pitch = (size_t)c->pitchf * 4; es = 4; break;
+    }
+  } else if (id == B2C_BUF_EDGES) {
+    p = c->d_edges; pitch = c->edges_pitch;
+  } else if (id == B2C_BUF_MAP2) {
+    p = c->d_map2; pitch = (size_t)c->map_pitch * 4; es = 4;
+  } else if (id == B2C_BUF_BITS) {
+    p = S0(c); pitch = (size_t)c->plane_pitch * 4; es = 4;
+  } else if (id == B2C_BUF_VIEW) {
+    if (c->last_stage == B2C_STAGE_HYSTER) { p = c->d_edges; pitch = c->edges_pitch; }
+    else { p = c->d_view; pitch = (size_t)c->w; }
+  } else {
+    return B2C_ERR_INVALID;
+  }
+  *dev_ptr = p;
+  if (pitch_bytes) *pitch_bytes = pitch;
+  if (elem_size) *elem_size = es;
+  return B2C_OK;
+}
+
+int b2c_download(b2c_handle c, int id, void *host, size_t host_pitch)
+{
+  if (!c || !host) return B2C_ERR_INVALID;
+  const void *p;
+  size_t pitch;
+  int es;
+  int rc = b2c_get_buffer(c, id, &p, &pitch, &es);
+  if (rc != B2C_OK) return rc;
+  DevGuard g(c->dev);
+  size_t row;
+  if (id == B2C_BUF_MAP2) row = (size_t)c->map_pitch * 4;
+  else if (id == B2C_BUF_BITS) row = (size_t)c->wpr * 4;
+  else row = (size_t)c->w * es;
+  if (host_pitch == 0) host_pitch = row;
+  if (host_pitch < row) return B2C_ERR_SIZE;
+  CK(c, cudaStreamSynchronize(c->s_main));
+  CK(c, cudaMemcpy2D(host, host_pitch, p, pitch, row, c->rows_alloc, cudaMemcpyDeviceToHost));
+  return B2C_OK;
+}
+
+int b2c_dev_alloc(b2c_handle c, size_t bytes, void **dev_ptr)
+{
+  if (!c || !dev_ptr) return B2C_ERR_INVALID;
+  DevGuard g(c->dev);
+  CK(c, cudaMalloc(dev_ptr, bytes));
+  return B2C_OK;
+}
+int b2c_dev_free(b2c_handle c, void *p)
+{
+  if (!c) return B2C_ERR_INVALID;
+  DevGuard g(c->dev);
+  CK(c, cudaFree(p));
+  return B2C_OK;
+}
+int b2c_dev_upload(b2c_handle c, void *dst, const void *src, size_t bytes)
+{
+  if (!c || !dst || !src) return B2C_ERR_INVALID;
+  DevGuard g(c->dev);
+  CK(c, cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  return B2C_OK;
+}
+int b2c_dev_download(b2c_handle c, void *dst, const void *src, size_t bytes)
+{
+  if (!c || !dst || !src) return B2C_ERR_INVALID;
+  DevGuard g(c->dev);
+  CK(c, cudaStreamSynchronize(c->s_main));
+  CK(c, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return B2C_OK;
+}
+int b2c_host_alloc(size_t bytes, void **host_ptr)
+{
+  if (!host_ptr) return B2C_ERR_INVALID;
+  if (cudaMallocHost(host_ptr, bytes) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return B2C_ERR_NOMEM;
+  }
+  return B2C_OK;
+}
+int b2c_host_free(void *p)
+{
+  if (cudaFreeHost(p) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return B2C_ERR_CUDA;
+  }
+  return B2C_OK;
+}
+int b2c_sync(b2c_handle c)
+{
+  if (!c) return B2C_ERR_INVALID;
+  DevGuard g(c->dev);
+  CK(c, cudaStreamSynchronize(c->s_main));
+  CK(c, cudaStreamSynchronize(c->s_h2d));
+  CK(c, cudaStreamSynchronize(c->s_d2h));
+  return B2C_OK;
+}
+void *b2c_stream(b2c_handle c) { return c ? (void *)c->s_main : nullptr; }
+
+// ---- row-band mode --------------------------------------------------------------------------------
+int b2c_band_stencil(b2c_handle c, const uint8_t *dev_bgr_band_row0, size_t row_stride, void *stream)
+{
+  if (!c || !c->band || !dev_bgr_band_row0) return B2C_ERR_INVALID;
+  if (row_stride < (size_t)c->w * 3) return B2C_ERR_SIZE;
+  DevGuard g(c->dev);
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->s_main;
+  c->have_frame = true;
+  return launch_stencil(c, dev_bgr_band_row0, row_stride, 0, 1, st);
+}
+
+int b2c_band_hysteresis(b2c_handle c, int first_call, int write_edges, int *changed, void *stream)
+{
+  if (!c || !c->band) return B2C_ERR_INVALID;
+  DevGuard g(c->dev);
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->s_main;
+  int rc = launch_hysteresis(c, 1, c->d_edges, c->edges_pitch, c->edges_frame_stride, first_call ? 0 : 1, write_edges ? 0 : 1, st);
+  if (rc != B2C_OK) return rc;
+  if (changed) {
+    CK(c, cudaMemcpyAsync(c->h_flags, c->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    *changed = c->h_flags[4];
+  }
+  return B2C_OK;
+}
+
+int b2c_band_boundary_ptr(b2c_handle c, int which, void **dev_ptr, int *words)
+{
+  if (!c || !c->band || !dev_ptr || which < 0 || which > 1) return B2C_ERR_INVALID;
+  *dev_ptr = S0(c) + (which == 0 ? 0 : (size_t)(c->rows_alloc - 1) * c->plane_pitch);
+  if (words) *words = c->wpr;
+  return B2C_OK;
+}
+int b2c_band_ghost_ptr(b2c_handle c, int which, void **dev_ptr, int *words)
+{
+  if (!c || !c->band || !dev_ptr || which < 0 || which > 1) return B2C_ERR_INVALID;
+  *dev_ptr = which == 0 ? c->d_S_base : S0(c) + (size_t)c->rows_alloc * c->plane_pitch;
+  if (words) *words = c->wpr;
+  return B2C_OK;
+}
+int b2c_band_flag_ptr(b2c_handle c, void **dev_ptr)
+{
+  if (!c || !dev_ptr) return B2C_ERR_INVALID;
+  *dev_ptr = c->d_flags + 4;
+  return B2C_OK;
+}
+
+// ---- misc -----------------------------------------------------------------------------------------
+const char *b2c_strerror(int s)
+{
+  switch (s) {
+  case B2C_OK: return "ok";
+  case B2C_ERR_INVALID: return "invalid argument";
+  case B2C_ERR_CUDA: return "CUDA error";
+  case B2C_ERR_NOMEM: return "out of memory";
+  case B2C_ERR_SIZE: return "frame geometry mismatch";
+  case B2C_ERR_UNSUPPORTED: return "unsupported";
+  case B2C_ERR_STATE: return "no frame has been run yet";
+  default: return "unknown status";
+  }
+}
+const char *b2c_last_cuda_error(b2c_handle c) { return c ? c->last_err.c_str() : ""; }
+const char *b2c_version(void) { return "b200canny 0.1 (sm_100a)"; }
+int b2c_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+long long b2c_launch_count(b2c_handle c) { return c ? c->launches : 0; }
+
+int b2c_set_option(b2c_handle c, const char *name, int value)
+{
+  if (!c || !name) return B2C_ERR_INVALID;
+  if (!strcmp(name, "stencil_impl")) {
+    if (value < 0 || value > 1) return B2C_ERR_INVALID;
+    c->stencil_impl = value;
+    return B2C_OK;
+  }
+  if (!strcmp(name, "hyst_max_rounds")) {
+    if (value < 1) return B2C_ERR_INVALID;
+    c->hyst_max_rounds = value;
+    return B2C_OK;
+  }
+  return B2C_ERR_INVALID;
+}
+int b2c_get_info(b2c_handle c, const char *name)
+{
+  if (!c || !name) return B2C_ERR_INVALID;
+  if (!strcmp(name, "hyst_rounds")) return c->h_flags[3];
+  if (!strcmp(name, "hyst_grid")) return c->hyst_grid;
+  if (!strcmp(name, "sm_count")) return c->sm_count;
+  if (!strcmp(name, "stencil_impl")) return c->stencil_impl;
+  if (!strcmp(name, "in_row_stride")) return (int)c->in_row_stride;
+  if (!strcmp(name, "plane_pitch_words")) return c->plane_pitch;
+  if (!strcmp(name, "map_pitch_words")) return c->map_pitch;
+  return B2C_ERR_INVALID;
+}
+
+}// extern "C"

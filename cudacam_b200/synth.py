@@ -1,0 +1,32 @@
+"""Deterministic synthetic BGR8 frames; thin wrapper over b2c_synth_frame (csrc/synth.cpp)."""
+import numpy as np
+
+from . import _lib
+
+KINDS = {"scene": 0, "noise": 1, "steps": 2}
+
+
+def frame(kind, seed, w, h, out=None):
+    """Returns an (h, w, 3) uint8 BGR frame."""
+    k = KINDS[kind] if isinstance(kind, str) else int(kind)
+    if out is None:
+        out = np.empty((h, w, 3), np.uint8)
+    assert out.dtype == np.uint8 and out.shape == (h, w, 3) and out.strides[2] == 1 and out.strides[1] == 3
+    _lib.check(_lib.lib.b2c_synth_frame(k, seed & (2**64 - 1), w, h, out.ctypes.data, out.strides[0]), what="b2c_synth_frame")
+    return out
+
+
+def stream_seed(stream, f):
+    """Seed of frame f of stream s."""
+    return 0xC0FFEE ^ (stream << 32) ^ f
+
+
+def batch(kind, n, w, h, stream=0, distinct=None):
+    """n frames (n, h, w, 3); only `distinct` different frames are generated, then tiled."""
+    distinct = n if distinct is None else min(distinct, n)
+    out = np.empty((n, h, w, 3), np.uint8)
+    for f in range(distinct):
+        frame(kind, stream_seed(stream, f), w, h, out[f])
+    for f in range(distinct, n):
+        out[f] = out[f % distinct]
+    return out

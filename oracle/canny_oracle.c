@@ -134,6 +134,23 @@ ORACLE_API int oracle_sector(int sumx, int sumy)
   return ((sumx > 0) == (sumy > 0)) ? 1 : 3;
 }
 
+/* Whole finite domain of the gradient stage: for every (sumx, sumy) in [-1020,1020]^2 (row = sumy+1020,
+ * col = sumx+1020) the sector and the NMS byte value (unsigned char)grad of a kept pixel
+ * (src/cvp/cannyEdgeD.cu:195,267).  tests/ compares both tables with what the reference's own gradSlope /
+ * nonMaxSuppr kernels produce on the GPU (tests/golden/tables.json holds the hashes of that run). */
+ORACLE_API void oracle_domain_tables(uint8_t *sector_out, uint8_t *nmsval_out)
+{
+  for (int j = 0; j < 2041; ++j)
+    for (int i = 0; i < 2041; ++i) {
+      const int gx = i - 1020, gy = j - 1020;
+      const float sx = (float)gx / 8.0f, sy = (float)gy / 8.0f;
+      float g;
+      oracle_grad(&sx, &sy, 1, &g);
+      if (sector_out) sector_out[(size_t)j * 2041 + i] = (uint8_t)oracle_sector(gx, gy);
+      if (nmsval_out) nmsval_out[(size_t)j * 2041 + i] = (uint8_t)((uint32_t)g & 0xFFu);
+    }
+}
+
 /* Best-effort float slope (correctly rounded double atan2 -> float).  Informational only: CUDA's
  * atan2f may differ by an ulp or two; parity is asserted on sectors, never on these bits. */
 ORACLE_API void oracle_slope(const float *sx, const float *sy, size_t n, float *slope)

@@ -1,0 +1,78 @@
+// emu_main.cpp -- TEST-ONLY: runs the product's kernel sources on the CPU through tests/emu/cuda_emu.h
+// (one OS thread per CUDA thread) so that kernel logic can be checked against the oracle without a GPU.
+// Never part of libb200canny.so.
+#define B2C_EMU 1
+#include "cuda_emu.h"
+
+#include "../../cudacam_b200/csrc/b2c_device.cuh"
+#include "../../cudacam_b200/csrc/k_hysteresis.cuh"
+#include "../../cudacam_b200/csrc/k_stencil_tile.cuh"
+#ifdef B2C_EMU_FUSED
+#include "../../cudacam_b200/csrc/k_stencil_fused.cuh"
+#endif
+
+static void fill_gk(float gk[25])
+{
+  static const float k[25] = { 2, 4, 5, 4, 2, 4, 9, 12, 9, 4, 5, 12, 15, 12, 5, 4, 9, 12, 9, 4, 2, 4, 5, 4, 2 };
+  const float inv = 1 / 159.0f;
+  for (int i = 0; i < 25; ++i) {
+    volatile float v = k[i] * inv;
+    gk[i] = v;
+  }
+}
+
+extern "C" {
+// impl: 1 = tile kernel (EMIT when any stage pointer is given), 0 = fused kernel
+__attribute__((visibility("default"))) int emu_stencil(int impl, const uint8_t *bgr, long long row_stride, long long frame_stride, int w, int h, int y0, int h_glob, int nframes,
+                                                       unsigned lo, unsigned hi, uint32_t *map2, uint8_t *mono, uint8_t *blur, float *grad, uint8_t *nms, uint8_t *thresh)
+{
+  B2cStencilParams p;
+  memset(&p, 0, sizeof(p));
+  p.bgr = bgr; p.row_stride = row_stride; p.frame_stride = frame_stride;
+  p.w = w; p.h = h; p.y0 = y0; p.h_glob = h_glob; p.nframes = nframes;
+  p.map2 = map2; p.map_pitch = (w + 15) / 16; p.map_frame_stride = (long long)h * p.map_pitch;
+  p.lo = lo; p.hi = hi;
+  fill_gk(p.gk);
+  p.mono = mono; p.blur = blur; p.grad = grad; p.nms = nms; p.thresh = thresh;
+  p.pitch8 = w; p.pitchf = w;
+  if (impl == 1) {
+    dim3 grid((w + b2c::TILE_W - 1) / b2c::TILE_W, (h + b2c::TILE_H - 1) / b2c::TILE_H, nframes);
+    if (mono || blur || grad || nms || thresh)
+      emu::launch(grid, dim3(b2c::TILE_THREADS), b2c::TILE_SMEM, false, [p] { b2c::k_stencil_tile<true>(p); });
+    else
+      emu::launch(grid, dim3(b2c::TILE_THREADS), b2c::TILE_SMEM, false, [p] { b2c::k_stencil_tile<false>(p); });
+    return 0;
+  }
+#ifdef B2C_EMU_FUSED
+  return b2c::fused_emu_launch(p);
+#else
+  return -1;
+#endif
+}
+
+// S/C planes are allocated here (with ghost rows); ghost_top/ghost_bot (wpr words each, may be null) seed the
+// ghost rows (row-band mode).  Returns rounds used; *changed = flags[4].
+__attribute__((visibility("default"))) int emu_hysteresis(const uint32_t *map2, int w, int h, int nframes, int grid_blocks, int tile_rows, uint8_t *edges, uint32_t *bits_out,
+                                                          const uint32_t *ghost_top, const uint32_t *ghost_bot, int *changed)
+{
+  const int wpr = (w + 31) / 32, pitch = (wpr + 3) / 4 * 4;
+  const long long fs = (long long)(h + 2) * pitch;
+  std::vector<uint32_t> S((size_t)fs * nframes, 0), Cc((size_t)fs * nframes, 0);
+  if (ghost_top) memcpy(S.data(), ghost_top, wpr * 4);
+  if (ghost_bot) memcpy(S.data() + (size_t)(h + 1) * pitch, ghost_bot, wpr * 4);
+  int flags[16] = { 0 };
+  B2cHystParams p;
+  memset(&p, 0, sizeof(p));
+  p.map2 = map2; p.map_pitch = (w + 15) / 16; p.map_frame_stride = (long long)h * p.map_pitch;
+  p.S = S.data() + pitch; p.C = Cc.data() + pitch; p.plane_pitch = pitch; p.plane_frame_stride = fs;
+  p.w = w; p.h = h; p.nframes = nframes;
+  p.edges = edges; p.edges_pitch = w; p.edges_frame_stride = (long long)w * h;
+  p.flags = flags; p.max_rounds = 1 << 20; p.tile_rows = tile_rows;
+  emu::launch(dim3(grid_blocks), dim3(b2c::HYST_THREADS), b2c::hyst_smem_bytes(tile_rows), true, [p] { b2c::k_hysteresis(p); });
+  if (bits_out)
+    for (int f = 0; f < nframes; ++f)
+      for (int y = 0; y < h; ++y) memcpy(bits_out + ((size_t)f * h + y) * wpr, p.S + f * fs + (long long)y * pitch, wpr * 4);
+  if (changed) *changed = flags[4];
+  return flags[3];
+}
+}

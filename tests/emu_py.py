@@ -1,0 +1,82 @@
+"""TEST-ONLY: loads tests/emu/libemu.so, the product's kernel sources compiled for the CPU through
+tests/emu/cuda_emu.h.  Lets `-m "not gpu"` tests check kernel logic against the oracle without a GPU."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU_DIR = os.path.join(HERE, "emu")
+EMU_SO = os.path.join(EMU_DIR, "libemu.so")
+_vp, _i, _ll = C.c_void_p, C.c_int, C.c_longlong
+
+
+def build(force=False):
+    srcs = [os.path.join(EMU_DIR, "emu_main.cpp"), os.path.join(EMU_DIR, "cuda_emu.h")]
+    csrc = os.path.join(os.path.dirname(HERE), "cudacam_b200", "csrc")
+    srcs += [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+    if not force and os.path.exists(EMU_SO) and all(os.path.getmtime(EMU_SO) >= os.path.getmtime(s) for s in srcs):
+        return
+    subprocess.check_call(["g++", "-std=c++20", "-O2", "-pthread", "-fPIC", "-shared", "-fvisibility=hidden", "-Wno-unused",
+                           "-DB2C_EMU_FUSED", "-I", EMU_DIR, "-o", EMU_SO, srcs[0]])
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(EMU_SO)
+        _lib.emu_stencil.restype = _i
+        _lib.emu_stencil.argtypes = [_i, _vp, _ll, _ll, _i, _i, _i, _i, _i, C.c_uint, C.c_uint, _vp, _vp, _vp, _vp, _vp, _vp]
+        _lib.emu_hysteresis.restype = _i
+        _lib.emu_hysteresis.argtypes = [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, C.POINTER(_i)]
+    return _lib
+
+
+def stencil(bgr, lo=10, hi=40, impl=1, stages=False, y0=0, h_glob=None, rows=None, row0=0):
+    """bgr (h, w, 3) or (n, h, w, 3).  In band mode pass the whole image plus row0/rows/y0/h_glob."""
+    a = np.ascontiguousarray(bgr, np.uint8)
+    if a.ndim == 3:
+        a = a[None]
+    n, hh, w, _ = a.shape
+    h = hh if rows is None else rows
+    h_glob = hh if h_glob is None else h_glob
+    gpr = (w + 15) // 16
+    map2 = np.zeros((n, h, gpr), np.uint32)
+    out = dict(map2=map2)
+    ptrs = [None] * 5
+    if stages:
+        out.update(mono=np.zeros((h, w), np.uint8), blur=np.zeros((h, w), np.uint8), grad=np.zeros((h, w), np.float32),
+                   nms=np.zeros((h, w), np.uint8), thresh=np.zeros((h, w), np.uint8))
+        ptrs = [out[k].ctypes.data for k in ("mono", "blur", "grad", "nms", "thresh")]
+    base = a.ctypes.data + row0 * a.strides[1]
+    rc = lib().emu_stencil(impl, base, a.strides[1], a.strides[0], w, h, y0, h_glob, n, lo, hi, map2.ctypes.data, *ptrs)
+    assert rc == 0, rc
+    return out
+
+
+def hysteresis(map2, w, grid_blocks=3, tile_rows=4, ghost_top=None, ghost_bot=None):
+    m = np.ascontiguousarray(map2, np.uint32)
+    if m.ndim == 2:
+        m = m[None]
+    n, h, _ = m.shape
+    edges = np.zeros((n, h, w), np.uint8)
+    bits = np.zeros((n, h, (w + 31) // 32), np.uint32)
+    ch = C.c_int(0)
+    gt = None if ghost_top is None else np.ascontiguousarray(ghost_top, np.uint32).ctypes.data
+    gb = None if ghost_bot is None else np.ascontiguousarray(ghost_bot, np.uint32).ctypes.data
+    rounds = lib().emu_hysteresis(m.ctypes.data, w, h, n, grid_blocks, tile_rows, edges.ctypes.data, bits.ctypes.data, gt, gb, C.byref(ch))
+    return edges, bits, rounds, ch.value
+
+
+def stencil_raw(buf, row0, w, h, lo=10, hi=40, impl=0, y0=0, h_glob=None):
+    """buf: 2-D uint8 array of padded rows; the frame starts at row `row0`.  Returns the 2-bit map or None if the
+    implementation is not available in the emulator build."""
+    h_glob = h if h_glob is None else h_glob
+    map2 = np.zeros((h, (w + 15) // 16), np.uint32)
+    rc = lib().emu_stencil(impl, buf.ctypes.data + row0 * buf.strides[0], buf.strides[0], 0, w, h, y0, h_glob, 1, lo, hi, map2.ctypes.data, None, None, None, None, None)
+    return map2 if rc == 0 else None

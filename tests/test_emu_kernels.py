@@ -1,0 +1,71 @@
+"""Kernel LOGIC on the CPU: the product's .cuh kernels compiled for the host through tests/emu/cuda_emu.h
+(one OS thread per CUDA thread, real barriers) and compared with the oracle.  This is not the product path
+(that is CUDA only, covered by the -m gpu tests); it catches indexing / synchronisation bugs without a GPU."""
+import numpy as np
+import pytest
+
+import emu_py as E
+import oracle_py as O
+from cudacam_b200 import synth
+
+CASES = [("scene", 200, 150, 7, 10, 40), ("noise", 97, 61, 8, 10, 40), ("steps", 130, 70, 9, 17, 43), ("scene", 16, 5, 3, 10, 40), ("noise", 1, 1, 1, 0, 0)]
+
+
+@pytest.mark.parametrize("kind,w,h,seed,lo,hi", CASES)
+def test_tile_stencil_all_stages(kind, w, h, seed, lo, hi):
+    f = synth.frame(kind, seed, w, h)
+    r = O.canny(f, lo, hi)
+    e = E.stencil(f, lo, hi, impl=1, stages=True)
+    for k in ("mono", "blur", "nms", "thresh"):
+        assert np.array_equal(e[k], r[k]), k
+    assert np.array_equal(e["grad"].view(np.uint32), r["grad"].view(np.uint32))
+    assert np.array_equal(e["map2"][0], O.thresh_to_map2(r["thresh"]))
+
+
+@pytest.mark.parametrize("kind,w,h,seed,lo,hi", CASES[:4])
+def test_fused_stencil_map(kind, w, h, seed, lo, hi):
+    f = synth.frame(kind, seed, w, h)
+    r = O.canny(f, lo, hi, want_edges=False)
+    # the fused kernel wants 16-byte aligned rows: give it a padded copy like the host driver does
+    stride = (w * 3 + 15) // 16 * 16
+    buf = np.zeros((h + 8, stride), np.uint8)
+    buf[4:4 + h, :w * 3] = f.reshape(h, w * 3)
+    e = E.stencil_raw(buf, 4, w, h, lo, hi, impl=0)
+    if e is None:
+        pytest.skip("fused kernel not in the emulator build")
+    assert np.array_equal(e, O.thresh_to_map2(r["thresh"]))
+
+
+@pytest.mark.parametrize("kind,w,h,seed", [("scene", 200, 150, 7), ("noise", 97, 61, 8), ("steps", 130, 70, 9), ("scene", 1100, 40, 5)])
+def test_hysteresis_kernel(kind, w, h, seed):
+    f = synth.frame(kind, seed, w, h)
+    r = O.canny(f)
+    edges, bits, rounds, changed = E.hysteresis(O.thresh_to_map2(r["thresh"]), w, grid_blocks=3, tile_rows=4)
+    assert np.array_equal(edges[0], r["edges"])
+    assert np.array_equal(bits[0], O.edges_to_bits(r["edges"]))
+
+
+def test_hysteresis_long_chain_and_batch():
+    # a weak spiral seeded by a single strong pixel: worst case for tile-local propagation
+    w, h = 70, 40
+    t = np.zeros((h, w), np.uint8)
+    t[2, 2:w - 2] = 128
+    t[2:h - 2, w - 3] = 128
+    t[h - 3, 4:w - 2] = 128
+    t[6:h - 2, 4] = 128
+    t[6, 4:w - 6] = 128
+    t[2, 2] = 255
+    t[20, 30] = 128   # isolated weak pixel: must vanish
+    m = np.stack([O.thresh_to_map2(t), O.thresh_to_map2(np.zeros_like(t))])
+    edges, bits, rounds, changed = E.hysteresis(m, w, grid_blocks=2, tile_rows=4)
+    assert np.array_equal(edges[0], O.hysteresis(t)) and edges[0][20, 30] == 0 and edges[0][6, w - 7] == 255
+    assert not edges[1].any()
+
+
+def test_band_mode_stencil_equals_whole_image():
+    w, h = 150, 90
+    f = synth.frame("scene", 21, w, h)
+    whole = E.stencil(f, impl=1)["map2"][0]
+    y0, rows = 30, 25
+    band = E.stencil(f, impl=1, y0=y0, h_glob=h, rows=rows, row0=y0)["map2"][0]
+    assert np.array_equal(band, whole[y0:y0 + rows])

@@ -1,0 +1,147 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle, the committed golden outputs of the
+reference's kernels, and -- live -- the reference's own kernels compiled unmodified (oracle/_ref/libcvpref.so)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import oracle_py as O
+import cudacam_b200 as cb
+from cudacam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FRAME_FILES = sorted(glob.glob(os.path.join(GOLD, "frame_*.npz")))
+
+
+def _check_all(c, f, r):
+    c.run(f, cb.CannyStage.HYSTER)
+    assert np.array_equal(c.edges(), r["edges"]), "edge map"
+    assert np.array_equal(c.view(), r["edges"])
+    assert np.array_equal(c.map2(), O.thresh_to_map2(r["thresh"])), "2-bit map"
+    assert np.array_equal(c.bits(), O.edges_to_bits(r["edges"])), "bit plane"
+    assert np.array_equal(c.mono(), r["mono"])
+    assert np.array_equal(c.blur(), r["blur"])
+    assert np.array_equal(c.gradient().view(np.uint32), r["grad"].view(np.uint32))
+    assert np.array_equal(c.nms(), r["nms"])
+    assert np.array_equal(c.thresh(), r["thresh"])
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("kind,w,h,seed,lo,hi", [
+    ("scene", 1280, 720, 0xC0FFEE, 10, 40),      # BASELINE config 1
+    ("scene", 1280, 720, 0xC0FFEE, 17, 43),      # thresholds of the reference's screenshot
+    ("noise", 641, 363, 2, 10, 40), ("steps", 800, 600, 3, 10, 40), ("steps", 333, 222, 4, 3, 200),
+    ("scene", 31, 33, 6, 10, 40), ("noise", 1, 1, 1, 10, 40), ("scene", 16, 1, 2, 10, 40), ("scene", 5, 300, 2, 10, 40),
+    ("scene", 1920, 1080, 5, 10, 40),
+])
+def test_frame_vs_oracle(impl, kind, w, h, seed, lo, hi):
+    f = synth.frame(kind, seed, w, h)
+    r = O.canny(f, lo, hi)
+    with cb.CannyEdge(w, h) as c:
+        c.set_option("stencil_impl", impl)
+        c.setHighThreshold(hi)
+        c.setLowThreshold(lo)
+        _check_all(c, f, r)
+
+
+@pytest.mark.parametrize("path", FRAME_FILES, ids=[os.path.basename(p) for p in FRAME_FILES])
+def test_frame_vs_golden(path):
+    from test_oracle import parse
+    kind, w, h, seed, lo, hi = parse(path)
+    g = np.load(path)
+    f = synth.frame(kind, seed, w, h)
+    with cb.CannyEdge(w, h) as c:
+        c.setHighThreshold(hi)
+        c.setLowThreshold(lo)
+        for stage in range(6):
+            c.run(f, stage)
+            assert np.array_equal(c.view(), g[f"pbo{stage}"]), f"stage {stage} view"
+        assert np.array_equal(c.edges(), g["hyster"])
+        assert np.array_equal(c.gradient().view(np.uint32), g["grad"].view(np.uint32))
+
+
+def test_live_reference_kernels_720p():
+    """BASELINE config 1: bit-exact to the reference's own cvp CUDA pipeline, run side by side on this GPU."""
+    w, h = 1280, 720
+    f = synth.frame("scene", 0xC0FFEE, w, h)
+    ref = O.CvpRef(w, h)
+    ref.run(f, 5)
+    it, flag, _ = ref.info()
+    assert flag == 0 and it < 100
+    with cb.CannyEdge(w, h) as c:
+        c.run(f)
+        assert np.array_equal(c.edges(), ref.get("hyster"))
+        assert np.array_equal(c.thresh(), ref.get("thresh"))
+        assert np.array_equal(c.nms(), ref.get("nms"))
+        assert np.array_equal(c.blur(), ref.get("blur"))
+        assert np.array_equal(c.mono(), ref.get("mono"))
+        assert np.array_equal(c.gradient().view(np.uint32), ref.get("grad").view(np.uint32))
+    ref.close()
+
+
+def test_strided_input_and_threshold_api():
+    w, h = 300, 200
+    big = np.zeros((h, 1024), np.uint8)
+    f = synth.frame("scene", 9, w, h)
+    big[:, :w * 3] = f.reshape(h, -1)
+    view = np.lib.stride_tricks.as_strided(big, (h, w, 3), (1024, 3, 1))
+    with cb.CannyEdge(w, h) as c:
+        assert (c.getLowThreshold(), c.getHighThreshold()) == (10, 40)   # cannyEdgeH.cu:22-23
+        c.setLowThreshold(200)
+        assert c.getLowThreshold() == 40                                  # clamped: cannyEdgeH.hpp:25
+        c.setHighThreshold(5)
+        assert c.getHighThreshold() == 40
+        c.setLowThreshold(10)
+        assert c.isKernelProfilingEnabled()                               # default ON: cannyEdgeH.cu:24
+        c.run(view)
+        assert np.array_equal(c.edges(), O.canny(f)["edges"])
+        t = c.lastTimings()
+        assert t["total"] > 0 and t["rounds"] >= 1
+        with pytest.raises(cb.B2cError):
+            c.run(np.zeros((h + 1, w, 3), np.uint8))
+
+
+def test_cvpipeline_surface():
+    w, h = 160, 120
+    f = synth.frame("scene", 3, w, h)
+    p = cb.CvPipeline(0, w, h, 3)
+    assert p.process(f, cb.CannyStage.HYSTER) is True
+    assert np.array_equal(p.output(), O.canny(f)["edges"])
+    assert p.process(np.zeros((0, 0, 3), np.uint8), cb.CannyStage.HYSTER) is False
+    assert p.process(None, cb.CannyStage.HYSTER) is False
+    assert p.process(f, cb.CannyStage.GRADIENT) is True
+    assert np.array_equal(p.output(), O.float2uchar(O.canny(f)["grad"]))
+
+
+def test_batch_host_pipeline_and_bits():
+    w, h, n = 320, 180, 11
+    frames = synth.batch("scene", n, w, h)
+    want = np.stack([O.canny(frames[i])["edges"] for i in range(n)])
+    with cb.CannyEdge(w, h, max_batch=4) as c:
+        got = c.run_batch(frames)
+        assert np.array_equal(got, want)
+        bits = c.run_batch(frames, packed_bits=True)
+        assert np.array_equal(bits, np.stack([O.edges_to_bits(want[i]) for i in range(n)]))
+    with cb.CannyEdge(w, h, max_batch=1) as c:
+        assert np.array_equal(c.run_batch(frames[:3]), want[:3])
+
+
+def test_full_size_properties_1080p_batch():
+    """BASELINE config 2 size (subset of the batch), checked through size-independent properties:
+    strong pixels survive, non-candidates never appear, re-running hysteresis on the result is idempotent,
+    and every frame equals the single-frame path."""
+    w, h, n = 1920, 1080, 8
+    frames = synth.batch("scene", n, w, h, distinct=4)
+    with cb.CannyEdge(w, h, max_batch=8) as c:
+        got = c.run_batch(frames)
+    with cb.CannyEdge(w, h) as c1:
+        for i in (0, 3, 7):
+            c1.run(frames[i])
+            assert np.array_equal(c1.edges(), got[i])
+            th = c1.thresh()
+            assert np.all(got[i][th == 255] == 255) and np.all(got[i][th == 0] == 0)
+            t2 = np.where(got[i] == 255, 255, np.where(th == 128, 128, 0)).astype(np.uint8)
+            assert np.array_equal(O.hysteresis(t2), got[i])
+    assert np.array_equal(got[0], got[4])   # frames 0 and 4 are the same picture
