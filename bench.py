@@ -207,7 +207,11 @@ def run_ours(args, wl):
     d_edges = torch.empty(n * h * w, dtype=torch.uint8, device="cuda")
     c = cb.CannyEdge(w, h, device=local, max_batch=max(n, 2))
     c.enableKernelProfiling(False)
-    st = torch.cuda.current_stream().cuda_stream
+    # a real (non-default) torch stream: its handle is what the C ABI launches on, and torch.cuda.Event records on it
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    st = tstream.cuda_stream
+    assert st != 0
     H = c._h
 
     def stencil():
