@@ -192,6 +192,11 @@ void fill_stencil_params(b2c_ctx *c, B2cStencilParams &p, const uint8_t *bgr, si
   p.lo = c->lo;
   p.hi = c->hi;
   fill_gk(p.gk);
+  for (int k = 0; k < 3; ++k) {
+    const float a = (float)(256 * k + c->lo + 1), b = (float)(256 * k + c->hi + 1);
+    p.n_lo[k] = 4.0f * a * a;   // exact: < 2^24
+    p.n_hi[k] = 4.0f * b * b;
+  }
   p.pitch8 = c->pitch8;
   p.pitchf = c->pitchf;
 }
@@ -201,8 +206,7 @@ int launch_stencil(b2c_ctx *c, const uint8_t *bgr, size_t row_stride, size_t fra
 {
   B2cStencilParams p;
   fill_stencil_params(c, p, bgr, row_stride, frame_stride, n);
-  const bool aligned = ((reinterpret_cast<uintptr_t>(bgr) | row_stride | frame_stride) & 15) == 0;
-  if (c->stencil_impl == 0 && aligned && b2c::fused_supported(p)) {
+  if (c->stencil_impl == 0 && b2c::fused_supported(p)) {
     cudaError_t e = b2c::fused_launch(p, c->sm_count, st);
     if (e != cudaSuccess) return set_err(c, e, "k_stencil_fused launch");
   } else {

@@ -45,6 +45,10 @@ struct B2cStencilParams {
   long long map_frame_stride;// u32 per frame
   unsigned lo, hi;           // thresholds (src/cvp/cannyEdgeH.cu:22-23, strict '>' cannyEdgeD.cu:290)
   float gk[25];              // k*(1/159.0f) rounded on the host (src/cvp/cannyEdgeH.cu:372-379)
+  // double threshold in the N = sumX^2+sumY^2 domain.  The reference thresholds v = (unsigned char)grad
+  // (cannyEdgeD.cu:267,290), grad = 0.5*sqrt(N); the cast wraps mod 256, and trunc(grad) >= m <=> N >= 4m^2, so
+  //   v > T  <=>  N in [n[0], 4*256^2) or [n[1], 4*512^2) or [n[2], inf),  n[k] = 4*(256k + T + 1)^2
+  float n_lo[3], n_hi[3];
   // optional per-stage outputs (frame 0 only; null = not written)
   uint8_t *mono, *blur, *nms, *thresh;
   float *grad;
@@ -67,6 +71,42 @@ struct B2cHystParams {
   int skip_init;             // 1 = S/C planes already built (row-band mode re-entry)
   int skip_expand;           // 1 = do not write edges (row-band mode intermediate rounds)
 };
+
+// ---- packed fp16x2 helpers (operands are the raw 32-bit patterns) -------------------------------------------
+// All values that pass through them are integers of magnitude <= 2048, which fp16 represents exactly, so
+// this arithmetic is exact integer arithmetic on two pixels per instruction.
+#ifdef B2C_EMU
+static inline uint32_t emu_pack_h2(_Float16 lo, _Float16 hi) { uint16_t a, b; memcpy(&a, &lo, 2); memcpy(&b, &hi, 2); return (uint32_t)a | ((uint32_t)b << 16); }
+static inline _Float16 emu_h_lo(uint32_t v) { uint16_t a = (uint16_t)v; _Float16 h; memcpy(&h, &a, 2); return h; }
+static inline _Float16 emu_h_hi(uint32_t v) { uint16_t a = (uint16_t)(v >> 16); _Float16 h; memcpy(&h, &a, 2); return h; }
+static inline uint32_t b2c_h2add(uint32_t a, uint32_t b) { return emu_pack_h2((_Float16)((float)emu_h_lo(a) + (float)emu_h_lo(b)), (_Float16)((float)emu_h_hi(a) + (float)emu_h_hi(b))); }
+static inline uint32_t b2c_h2sub(uint32_t a, uint32_t b) { return emu_pack_h2((_Float16)((float)emu_h_lo(a) - (float)emu_h_lo(b)), (_Float16)((float)emu_h_hi(a) - (float)emu_h_hi(b))); }
+static inline uint32_t b2c_h2fma2(uint32_t a, uint32_t c) { return emu_pack_h2((_Float16)(2.0f * (float)emu_h_lo(a) + (float)emu_h_lo(c)), (_Float16)(2.0f * (float)emu_h_hi(a) + (float)emu_h_hi(c))); }
+static inline float b2c_fhfma_ll(uint32_t a, uint32_t b, float c) { return fmaf((float)emu_h_lo(a), (float)emu_h_lo(b), c); }
+static inline float b2c_fhfma_hh(uint32_t a, uint32_t b, float c) { return fmaf((float)emu_h_hi(a), (float)emu_h_hi(b), c); }
+static inline uint32_t b2c_u2h_bits(unsigned v) { _Float16 h = (_Float16)(float)v; uint16_t a; memcpy(&a, &h, 2); return a; }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
+#else
+#include <cuda_fp16.h>
+__device__ __forceinline__ uint32_t b2c_h2add(uint32_t a, uint32_t b) { uint32_t r; asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t b2c_h2sub(uint32_t a, uint32_t b) { uint32_t r; asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+// 2*a + c
+__device__ __forceinline__ uint32_t b2c_h2fma2(uint32_t a, uint32_t c) { uint32_t r; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(0x40004000u), "r"(c)); return r; }
+// fp32 <- half * half + fp32 (sm_100 mixed-precision FMA, SASS FHFMA with free .H0/.H1 operand select)
+__device__ __forceinline__ float b2c_fhfma_ll(uint32_t a, uint32_t b, float c)
+{
+  float r;
+  asm("{.reg .f16 al, ah, bl, bh; mov.b32 {al, ah}, %1; mov.b32 {bl, bh}, %2; fma.rn.f32.f16 %0, al, bl, %3;}" : "=f"(r) : "r"(a), "r"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float b2c_fhfma_hh(uint32_t a, uint32_t b, float c)
+{
+  float r;
+  asm("{.reg .f16 al, ah, bl, bh; mov.b32 {al, ah}, %1; mov.b32 {bl, bh}, %2; fma.rn.f32.f16 %0, ah, bh, %3;}" : "=f"(r) : "r"(a), "r"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t b2c_u2h_bits(unsigned v) { return (uint32_t)__half_as_ushort(__uint2half_rn(v)); }
+#endif
 
 // Exact sector of the gradient direction from the integer Sobel sums -- same rule as
 // oracle_sector() (pinned to the reference's atan2f path on the GPU, see tests/).

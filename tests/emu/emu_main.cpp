@@ -33,6 +33,11 @@ __attribute__((visibility("default"))) int emu_stencil(int impl, const uint8_t *
   p.map2 = map2; p.map_pitch = (w + 15) / 16; p.map_frame_stride = (long long)h * p.map_pitch;
   p.lo = lo; p.hi = hi;
   fill_gk(p.gk);
+  for (int k = 0; k < 3; ++k) {
+    const float a = (float)(256 * k + lo + 1), b = (float)(256 * k + hi + 1);
+    p.n_lo[k] = 4.0f * a * a;
+    p.n_hi[k] = 4.0f * b * b;
+  }
   p.mono = mono; p.blur = blur; p.grad = grad; p.nms = nms; p.thresh = thresh;
   p.pitch8 = w; p.pitchf = w;
   if (impl == 1) {

@@ -22,7 +22,11 @@ def test_tile_stencil_all_stages(kind, w, h, seed, lo, hi):
     assert np.array_equal(e["map2"][0], O.thresh_to_map2(r["thresh"]))
 
 
-@pytest.mark.parametrize("kind,w,h,seed,lo,hi", CASES[:4])
+FUSED_CASES = [("scene", 200, 150, 7, 10, 40), ("noise", 96, 61, 8, 10, 40), ("steps", 136, 70, 9, 17, 43), ("scene", 16, 5, 3, 10, 40),
+               ("steps", 480, 130, 2, 3, 200), ("scene", 8, 8, 1, 0, 0), ("noise", 488, 64, 3, 10, 40), ("scene", 720, 64, 3, 10, 40)]
+
+
+@pytest.mark.parametrize("kind,w,h,seed,lo,hi", FUSED_CASES)
 def test_fused_stencil_map(kind, w, h, seed, lo, hi):
     f = synth.frame(kind, seed, w, h)
     r = O.canny(f, lo, hi, want_edges=False)
@@ -69,3 +73,26 @@ def test_band_mode_stencil_equals_whole_image():
     y0, rows = 30, 25
     band = E.stencil(f, impl=1, y0=y0, h_glob=h, rows=rows, row0=y0)["map2"][0]
     assert np.array_equal(band, whole[y0:y0 + rows])
+
+
+@pytest.mark.parametrize("v", [0, 3, 100, 255])
+def test_fused_flat_picture_takes_dense_replay(v):
+    """Flat regions make S % 159 == 0 for every pixel: the work list overflows and the dense replay runs."""
+    f = np.full((70, 248, 3), v, np.uint8)
+    f[30:40, 100:140] = (v + 60) % 256
+    r = O.canny(f, 10, 40, want_edges=False)
+    buf = np.zeros((78, 752), np.uint8)
+    buf[4:74, :744] = f.reshape(70, -1)
+    e = E.stencil_raw(buf, 4, 248, 70, 10, 40, impl=0)
+    assert e is not None and np.array_equal(e, O.thresh_to_map2(r["thresh"]))
+
+
+def test_fused_band_mode_equals_whole_image():
+    w, h = 248, 150
+    f = synth.frame("scene", 23, w, h)
+    whole = O.thresh_to_map2(O.canny(f, want_edges=False)["thresh"])
+    buf = np.zeros((h, 752), np.uint8)
+    buf[:, :w * 3] = f.reshape(h, -1)
+    for y0, rows in ((0, 50), (50, 61), (111, 39)):
+        band = E.stencil_raw(buf, y0, w, rows, impl=0, y0=y0, h_glob=h)
+        assert np.array_equal(band, whole[y0:y0 + rows]), (y0, rows)
