@@ -21,6 +21,7 @@
 #include "../../include/b200canny.h"
 #include "b2c_device.cuh"
 #include "k_hysteresis.cuh"
+#include "k_hysteresis_uf.cuh"
 #include "k_stencil_fused.cuh"
 #include "k_stencil_tile.cuh"
 #include "k_views.cuh"
@@ -41,6 +42,7 @@ struct b2c_ctx {
   uint8_t lo = 10, hi = 40;   // src/cvp/cannyEdgeH.cu:22-23
   bool profiling = true;      // src/cvp/cannyEdgeH.cu:24
   int stencil_impl = 0;       // 0 fused, 1 tile
+  int hyst_impl = 0;          // 0 union-find (constant number of phases), 1 tile rounds
   int hyst_tile_rows = 16;
   int hyst_max_rounds = 1 << 20;
 
@@ -61,6 +63,8 @@ struct b2c_ctx {
   uint8_t *d_mono = nullptr, *d_blur = nullptr, *d_nms = nullptr, *d_thresh = nullptr, *d_view = nullptr;
   float *d_grad = nullptr;
   int *d_flags = nullptr;
+  int *d_parent = nullptr;
+  int uf_grid = 0;
   int *h_flags = nullptr;   // pinned mirror
 
   // last input (for on-demand stage buffers)
@@ -146,6 +150,7 @@ int alloc_common(b2c_ctx *c)
   CK(c, cudaMemset(c->d_S_base, 0, plane_bytes));
   CK(c, cudaMemset(c->d_C_base, 0, plane_bytes));
   CK(c, cudaMalloc(&c->d_edges, (size_t)nb * c->edges_frame_stride));
+  CK(c, cudaMalloc(&c->d_parent, (size_t)nb * rows * c->plane_pitch * 32 * sizeof(int)));
   CK(c, cudaMalloc(&c->d_flags, 16 * sizeof(int)));
   CK(c, cudaMemset(c->d_flags, 0, 16 * sizeof(int)));
   CK(c, cudaMallocHost(&c->h_flags, 16 * sizeof(int)));
@@ -170,6 +175,12 @@ int alloc_common(b2c_ctx *c)
     return B2C_ERR_CUDA;
   }
   c->hyst_grid = c->sm_count * std::min(per_sm, 4);
+  CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b2c::k_hysteresis_uf, b2c::UF_THREADS, 0));
+  if (per_sm < 1) {
+    c->last_err = "union-find hysteresis kernel does not fit on an SM";
+    return B2C_ERR_CUDA;
+  }
+  c->uf_grid = c->sm_count * per_sm;
   CK(c, cudaFuncSetAttribute(b2c::k_stencil_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2c::TILE_SMEM));
   CK(c, cudaFuncSetAttribute(b2c::k_stencil_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2c::TILE_SMEM));
   return b2c::fused_configure() == cudaSuccess ? B2C_OK : set_err(c, cudaGetLastError(), "fused_configure");
@@ -267,8 +278,17 @@ int launch_hysteresis(b2c_ctx *c, int n, uint8_t *edges, size_t edges_pitch, siz
   p.tile_rows = c->hyst_tile_rows;
   p.skip_init = skip_init;
   p.skip_expand = skip_expand;
+  p.parent = c->d_parent;
+  p.parent_frame_stride = (long long)c->rows_alloc * c->plane_pitch * 32;
   void *args[] = { &p };
-  CK(c, cudaLaunchCooperativeKernel((const void *)b2c::k_hysteresis, dim3(c->hyst_grid), dim3(b2c::HYST_THREADS), args, (size_t)c->hyst_smem, st));
+  if (c->hyst_impl == 0) {
+    // enough CTAs to cover the plane words once, at most one full wave
+    const long long words = (long long)n * c->rows_alloc * c->wpr;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(c->uf_grid, (words + b2c::UF_THREADS - 1) / b2c::UF_THREADS));
+    CK(c, cudaLaunchCooperativeKernel((const void *)b2c::k_hysteresis_uf, dim3(grid), dim3(b2c::UF_THREADS), args, 0, st));
+  } else {
+    CK(c, cudaLaunchCooperativeKernel((const void *)b2c::k_hysteresis, dim3(c->hyst_grid), dim3(b2c::HYST_THREADS), args, (size_t)c->hyst_smem, st));
+  }
   c->launches++;
   return B2C_OK;
 }
@@ -373,6 +393,7 @@ void b2c_destroy(b2c_handle c)
   cudaFree(c->d_view);
   cudaFree(c->d_grad);
   cudaFree(c->d_flags);
+  cudaFree(c->d_parent);
   if (c->h_flags) cudaFreeHost(c->h_flags);
   for (int i = 0; i < NSLOT; ++i) {
     if (c->h_in[i]) cudaFreeHost(c->h_in[i]);
@@ -835,6 +856,11 @@ int b2c_set_option(b2c_handle c, const char *name, int value)
   if (!strcmp(name, "stencil_impl")) {
     if (value < 0 || value > 1) return B2C_ERR_INVALID;
     c->stencil_impl = value;
+    return B2C_OK;
+  }
+  if (!strcmp(name, "hyst_impl")) {
+    if (value < 0 || value > 1) return B2C_ERR_INVALID;
+    c->hyst_impl = value;
     return B2C_OK;
   }
   if (!strcmp(name, "hyst_max_rounds")) {

@@ -70,6 +70,8 @@ struct B2cHystParams {
   int tile_rows;
   int skip_init;             // 1 = S/C planes already built (row-band mode re-entry)
   int skip_expand;           // 1 = do not write edges (row-band mode intermediate rounds)
+  int *parent;               // union-find parents, one int per pixel of the padded plane (only weak pixels are used)
+  long long parent_frame_stride;
 };
 
 // ---- packed fp16x2 helpers (operands are the raw 32-bit patterns) -------------------------------------------

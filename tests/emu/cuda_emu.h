@@ -204,6 +204,12 @@ template <class T> static inline T atomicMax(T *p, T v)
   while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
   return old;
 }
+template <class T> static inline T atomicMin(T *p, T v)
+{
+  T old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (old > v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
 template <class T> static inline T atomicCAS(T *p, T cmp, T v)
 {
   __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);

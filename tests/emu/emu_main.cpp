@@ -6,6 +6,7 @@
 
 #include "../../cudacam_b200/csrc/b2c_device.cuh"
 #include "../../cudacam_b200/csrc/k_hysteresis.cuh"
+#include "../../cudacam_b200/csrc/k_hysteresis_uf.cuh"
 #include "../../cudacam_b200/csrc/k_stencil_tile.cuh"
 #ifdef B2C_EMU_FUSED
 #include "../../cudacam_b200/csrc/k_stencil_fused.cuh"
@@ -73,7 +74,12 @@ __attribute__((visibility("default"))) int emu_hysteresis(const uint32_t *map2, 
   p.w = w; p.h = h; p.nframes = nframes;
   p.edges = edges; p.edges_pitch = w; p.edges_frame_stride = (long long)w * h;
   p.flags = flags; p.max_rounds = 1 << 20; p.tile_rows = tile_rows;
-  emu::launch(dim3(grid_blocks), dim3(b2c::HYST_THREADS), b2c::hyst_smem_bytes(tile_rows), true, [p] { b2c::k_hysteresis(p); });
+  std::vector<int> parent((size_t)nframes * h * pitch * 32, -12345);
+  p.parent = parent.data(); p.parent_frame_stride = (long long)h * pitch * 32;
+  if (tile_rows > 0)
+    emu::launch(dim3(grid_blocks), dim3(b2c::HYST_THREADS), b2c::hyst_smem_bytes(tile_rows), true, [p] { b2c::k_hysteresis(p); });
+  else   // tile_rows == 0 selects the union-find kernel
+    emu::launch(dim3(grid_blocks), dim3(b2c::UF_THREADS), 0, true, [p] { b2c::k_hysteresis_uf(p); });
   if (bits_out)
     for (int f = 0; f < nframes; ++f)
       for (int y = 0; y < h; ++y) memcpy(bits_out + ((size_t)f * h + y) * wpr, p.S + f * fs + (long long)y * pitch, wpr * 4);

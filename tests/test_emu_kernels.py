@@ -40,16 +40,27 @@ def test_fused_stencil_map(kind, w, h, seed, lo, hi):
     assert np.array_equal(e, O.thresh_to_map2(r["thresh"]))
 
 
+@pytest.mark.parametrize("tile_rows", [0, 4], ids=["unionfind", "tilerounds"])
 @pytest.mark.parametrize("kind,w,h,seed", [("scene", 200, 150, 7), ("noise", 97, 61, 8), ("steps", 130, 70, 9), ("scene", 1100, 40, 5)])
-def test_hysteresis_kernel(kind, w, h, seed):
+def test_hysteresis_kernel(kind, w, h, seed, tile_rows):
     f = synth.frame(kind, seed, w, h)
     r = O.canny(f)
-    edges, bits, rounds, changed = E.hysteresis(O.thresh_to_map2(r["thresh"]), w, grid_blocks=3, tile_rows=4)
+    edges, bits, rounds, changed = E.hysteresis(O.thresh_to_map2(r["thresh"]), w, grid_blocks=3, tile_rows=tile_rows)
     assert np.array_equal(edges[0], r["edges"])
     assert np.array_equal(bits[0], O.edges_to_bits(r["edges"]))
 
 
-def test_hysteresis_long_chain_and_batch():
+@pytest.mark.parametrize("dens", [0.1, 0.3, 0.5])
+def test_hysteresis_unionfind_random_maps(dens):
+    rng = np.random.default_rng(int(dens * 10))
+    t = np.where(rng.random((90, 131)) < dens, 128, 0).astype(np.uint8)
+    t[rng.random(t.shape) < 0.002] = 255
+    edges, _, _, _ = E.hysteresis(O.thresh_to_map2(t), 131, grid_blocks=4, tile_rows=0)
+    assert np.array_equal(edges[0], O.hysteresis(t))
+
+
+@pytest.mark.parametrize("tile_rows", [0, 4], ids=["unionfind", "tilerounds"])
+def test_hysteresis_long_chain_and_batch(tile_rows):
     # a weak spiral seeded by a single strong pixel: worst case for tile-local propagation
     w, h = 70, 40
     t = np.zeros((h, w), np.uint8)
@@ -61,7 +72,7 @@ def test_hysteresis_long_chain_and_batch():
     t[2, 2] = 255
     t[20, 30] = 128   # isolated weak pixel: must vanish
     m = np.stack([O.thresh_to_map2(t), O.thresh_to_map2(np.zeros_like(t))])
-    edges, bits, rounds, changed = E.hysteresis(m, w, grid_blocks=2, tile_rows=4)
+    edges, bits, rounds, changed = E.hysteresis(m, w, grid_blocks=2, tile_rows=tile_rows)
     assert np.array_equal(edges[0], O.hysteresis(t)) and edges[0][20, 30] == 0 and edges[0][6, w - 7] == 255
     assert not edges[1].any()
 

@@ -81,6 +81,25 @@ def test_live_reference_kernels_720p():
     ref.close()
 
 
+@pytest.mark.parametrize("hyst_impl", [0, 1], ids=["unionfind", "tilerounds"])
+def test_hysteresis_impls_and_worst_cases(hyst_impl):
+    """Both on-device hysteresis schemes against the fixpoint oracle, incl. a 1910-px weak line seeded at one end
+    (65 reference launches) and a dense random map."""
+    w, h = 1920, 64
+    f = synth.frame("scene", 77, w, h)
+    with cb.CannyEdge(w, h) as c:
+        c.set_option("hyst_impl", hyst_impl)
+        c.run(f)
+        assert np.array_equal(c.edges(), O.canny(f)["edges"])
+    for kind, ww, hh, seed in (("noise", 640, 360, 5), ("steps", 800, 600, 6), ("scene", 3840, 2160, 9)):
+        f = synth.frame(kind, seed, ww, hh)
+        with cb.CannyEdge(ww, hh) as c:
+            c.set_option("hyst_impl", hyst_impl)
+            c.run(f)
+            th = c.thresh()
+            assert np.array_equal(c.edges(), O.hysteresis(th)), (kind, ww, hh)
+
+
 def test_strided_input_and_threshold_api():
     w, h = 300, 200
     big = np.zeros((h, 1024), np.uint8)
