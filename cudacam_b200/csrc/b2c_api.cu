@@ -175,7 +175,7 @@ int alloc_common(b2c_ctx *c)
     return B2C_ERR_CUDA;
   }
   c->hyst_grid = c->sm_count * std::min(per_sm, 4);
-  CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b2c::k_hysteresis_uf, b2c::UF_THREADS, 0));
+  CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b2c::k_hysteresis_uf, b2c::UF_THREADS, b2c::UF_SMEM));
   if (per_sm < 1) {
     c->last_err = "union-find hysteresis kernel does not fit on an SM";
     return B2C_ERR_CUDA;
@@ -282,10 +282,11 @@ int launch_hysteresis(b2c_ctx *c, int n, uint8_t *edges, size_t edges_pitch, siz
   p.parent_frame_stride = (long long)c->rows_alloc * c->plane_pitch * 32;
   void *args[] = { &p };
   if (c->hyst_impl == 0) {
-    // enough CTAs to cover the plane words once, at most one full wave
-    const long long words = (long long)n * c->rows_alloc * c->wpr;
-    const int grid = (int)std::max<long long>(1, std::min<long long>(c->uf_grid, (words + b2c::UF_THREADS - 1) / b2c::UF_THREADS));
-    CK(c, cudaLaunchCooperativeKernel((const void *)b2c::k_hysteresis_uf, dim3(grid), dim3(b2c::UF_THREADS), args, 0, st));
+    // one warp per plane row, at most one full wave of CTAs
+    const long long rows = (long long)n * c->rows_alloc;
+    const int wpb = b2c::UF_THREADS / 32;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(c->uf_grid, (rows + wpb - 1) / wpb));
+    CK(c, cudaLaunchCooperativeKernel((const void *)b2c::k_hysteresis_uf, dim3(grid), dim3(b2c::UF_THREADS), args, (size_t)b2c::UF_SMEM, st));
   } else {
     CK(c, cudaLaunchCooperativeKernel((const void *)b2c::k_hysteresis, dim3(c->hyst_grid), dim3(b2c::HYST_THREADS), args, (size_t)c->hyst_smem, st));
   }
@@ -874,6 +875,12 @@ int b2c_get_info(b2c_handle c, const char *name)
 {
   if (!c || !name) return B2C_ERR_INVALID;
   if (!strcmp(name, "hyst_rounds")) return c->h_flags[3];
+  if (!strncmp(name, "stamp", 5)) {   // phase time stamps of the last hysteresis launch (ns, low 32 bits); debugging aid
+    int v[16];
+    if (cudaMemcpy(v, c->d_flags, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return B2C_ERR_CUDA;
+    const int k = name[5] - '0';
+    return (k >= 0 && k < 8) ? v[8 + k] : B2C_ERR_INVALID;
+  }
   if (!strcmp(name, "hyst_grid")) return c->hyst_grid;
   if (!strcmp(name, "sm_count")) return c->sm_count;
   if (!strcmp(name, "stencil_impl")) return c->stencil_impl;

@@ -79,7 +79,7 @@ __attribute__((visibility("default"))) int emu_hysteresis(const uint32_t *map2, 
   if (tile_rows > 0)
     emu::launch(dim3(grid_blocks), dim3(b2c::HYST_THREADS), b2c::hyst_smem_bytes(tile_rows), true, [p] { b2c::k_hysteresis(p); });
   else   // tile_rows == 0 selects the union-find kernel
-    emu::launch(dim3(grid_blocks), dim3(b2c::UF_THREADS), 0, true, [p] { b2c::k_hysteresis_uf(p); });
+    emu::launch(dim3(grid_blocks), dim3(b2c::UF_THREADS), b2c::UF_SMEM, true, [p] { b2c::k_hysteresis_uf(p); });
   if (bits_out)
     for (int f = 0; f < nframes; ++f)
       for (int y = 0; y < h; ++y) memcpy(bits_out + ((size_t)f * h + y) * wpr, p.S + f * fs + (long long)y * pitch, wpr * 4);

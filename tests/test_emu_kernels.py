@@ -107,3 +107,12 @@ def test_fused_band_mode_equals_whole_image():
     for y0, rows in ((0, 50), (50, 61), (111, 39)):
         band = E.stencil_raw(buf, y0, w, rows, impl=0, y0=y0, h_glob=h)
         assert np.array_equal(band, whole[y0:y0 + rows]), (y0, rows)
+
+
+def test_hysteresis_unionfind_word_list_overflow():
+    """More words with weak pixels per warp than the per-warp list holds: the kernel falls back to the plain scan."""
+    rng = np.random.default_rng(5)
+    t = np.where(rng.random((80, 2048)) < 0.2, 128, 0).astype(np.uint8)
+    t[rng.random(t.shape) < 0.001] = 255
+    edges, _, _, _ = E.hysteresis(O.thresh_to_map2(t), 2048, grid_blocks=1, tile_rows=0)
+    assert np.array_equal(edges[0], O.hysteresis(t))
