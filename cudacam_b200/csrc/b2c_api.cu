@@ -64,6 +64,7 @@ struct b2c_ctx {
   float *d_grad = nullptr;
   int *d_flags = nullptr;
   int *d_parent = nullptr;
+  uint8_t *d_zeros = nullptr;
   int uf_grid = 0;
   int *h_flags = nullptr;   // pinned mirror
 
@@ -151,6 +152,8 @@ int alloc_common(b2c_ctx *c)
   CK(c, cudaMemset(c->d_C_base, 0, plane_bytes));
   CK(c, cudaMalloc(&c->d_edges, (size_t)nb * c->edges_frame_stride));
   CK(c, cudaMalloc(&c->d_parent, (size_t)nb * rows * c->plane_pitch * 32 * sizeof(int)));
+  CK(c, cudaMalloc(&c->d_zeros, 256));
+  CK(c, cudaMemset(c->d_zeros, 0, 256));
   CK(c, cudaMalloc(&c->d_flags, 16 * sizeof(int)));
   CK(c, cudaMemset(c->d_flags, 0, 16 * sizeof(int)));
   CK(c, cudaMallocHost(&c->h_flags, 16 * sizeof(int)));
@@ -190,6 +193,7 @@ void fill_stencil_params(b2c_ctx *c, B2cStencilParams &p, const uint8_t *bgr, si
 {
   memset(&p, 0, sizeof(p));
   p.bgr = bgr;
+  p.zeros = c->d_zeros;
   p.row_stride = (long long)row_stride;
   p.frame_stride = (long long)frame_stride;
   p.w = c->w;
@@ -395,6 +399,7 @@ void b2c_destroy(b2c_handle c)
   cudaFree(c->d_grad);
   cudaFree(c->d_flags);
   cudaFree(c->d_parent);
+  cudaFree(c->d_zeros);
   if (c->h_flags) cudaFreeHost(c->h_flags);
   for (int i = 0; i < NSLOT; ++i) {
     if (c->h_in[i]) cudaFreeHost(c->h_in[i]);

@@ -34,6 +34,7 @@ enum { B2C_MONO = 0, B2C_GAUSSIAN = 1, B2C_GRADIENT = 2, B2C_NMS = 3, B2C_THRESH
 
 struct B2cStencilParams {
   const uint8_t *bgr;        // frame 0, band row 0 (rows -4.. may be read in band mode)
+  const uint8_t *zeros;      // >= 64 zero bytes, 16-byte aligned: what lanes outside the image read
   long long row_stride;      // bytes
   long long frame_stride;    // bytes
   int w, h;                  // width, rows produced by this launch

@@ -95,6 +95,18 @@ __device__ __forceinline__ void nms_item(const B2cStencilParams &p, char *smem, 
   }
 }
 
+// append one 16-bit item to the CTA's work list (plain shared-memory atomic, no warp aggregation)
+__device__ __forceinline__ void list_push(char *smem, int which, uint32_t item)
+{
+#ifdef B2C_EMU
+  const int idx = atomicAdd(reinterpret_cast<int *>(smem + FS_CNT) + which, 1);
+#else
+  int idx;
+  asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(idx) : "r"((unsigned)__cvta_generic_to_shared(smem + FS_CNT + 4 * which)) : "memory");
+#endif
+  if (idx < FT_LIST_CAP) reinterpret_cast<uint16_t *>(smem + FS_LIST)[idx] = (uint16_t)item;
+}
+
 __global__ void __launch_bounds__(FT_THREADS, 2) k_stencil_fused(const B2cStencilParams p)
 {
   B2C_DYN_SMEM(smem);
@@ -102,27 +114,34 @@ __global__ void __launch_bounds__(FT_THREADS, 2) k_stencil_fused(const B2cStenci
   const int X0 = blockIdx.x * FT_X, Y0 = blockIdx.y * FT_Y, frame = blockIdx.z;
   const int xl = X0 - 8 + 8 * lane;              // first pixel column of this lane
   const bool lane_in = xl >= 0 && xl < p.w;      // w % 8 == 0: a lane is wholly inside or wholly outside
-  const uint8_t *src = p.bgr + (long long)frame * p.frame_stride;
+  // CTA-uniform: does the 256-column window leave the image on either side?  Only then do lanes need masking.
+  const bool xborder = X0 == 0 || X0 + 248 > p.w;
+  const uint32_t lane_mask = lane_in ? 0xFFFFFFFFu : 0u;
+  const int yg0 = Y0 + p.y0;                     // global row of tile row 0
   int *cnt = reinterpret_cast<int *>(smem + FS_CNT);
   uint32_t *s_out = reinterpret_cast<uint32_t *>(smem + FS_OUT);
-  uint16_t *list = reinterpret_cast<uint16_t *>(smem + FS_LIST);
+  const uint16_t *list = reinterpret_cast<const uint16_t *>(smem + FS_LIST);
 
   for (int i = tid; i < FT_Y * FT_OUTW; i += FT_THREADS) s_out[i] = 0;
   if (tid < 4) cnt[tid] = 0;
 
   // ---- stage 0: gray, rows Y0-4 .. Y0+63; zero outside the image (cannyEdgeD.cu:91-98) ----------------------
+  // Lanes outside the image read a block of zeros with stride 0, rows outside are skipped (warp-uniform).
   {
     constexpr int NR = (FT_MROWS + FT_WARPS - 1) / FT_WARPS;
+    const long long lstride = lane_in ? p.row_stride : 0;
+    const uint8_t *lp = lane_in ? p.bgr + (long long)frame * p.frame_stride + 3 * xl + (long long)(Y0 - 4 + warp) * p.row_stride : p.zeros;
     uint2 ld[NR][3];
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
-      const int ry = warp + FT_WARPS * i, y = Y0 - 4 + ry, yg = y + p.y0;
-      ld[i][0] = ld[i][1] = ld[i][2] = make_uint2(0u, 0u);
-      if (lane_in && ry < FT_MROWS && yg >= 0 && yg < p.h_glob) {
-        const uint2 *q = reinterpret_cast<const uint2 *>(src + (long long)y * p.row_stride + 3 * xl);
+      const int ry = warp + FT_WARPS * i, yg = yg0 - 4 + ry;
+      if (ry < FT_MROWS && yg >= 0 && yg < p.h_glob) {
+        const uint2 *q = reinterpret_cast<const uint2 *>(lp + (long long)(FT_WARPS * i) * lstride);
         ld[i][0] = __ldg(q);
         ld[i][1] = __ldg(q + 1);
         ld[i][2] = __ldg(q + 2);
+      } else {
+        ld[i][0] = ld[i][1] = ld[i][2] = make_uint2(0u, 0u);
       }
     }
 #pragma unroll
@@ -180,18 +199,24 @@ __global__ void __launch_bounds__(FT_THREADS, 2) k_stencil_fused(const B2cStenci
         vv[j] = V;
         hq[j] = b2c_h2sub(__byte_perm(V, U, 0x7632), 0x64006400u);       // (q_lo, q_hi) as exact fp16
       }
-      const uint32_t f01 = __byte_perm(__byte_perm(vv[0], uu[0], 0x5151), __byte_perm(vv[1], uu[1], 0x5151), 0x5410);
-      const uint32_t f23 = __byte_perm(__byte_perm(vv[2], uu[2], 0x5151), __byte_perm(vv[3], uu[3], 0x5151), 0x5410);
-      const int y = Y0 - 2 + br, yg = y + p.y0;
-      const bool in = lane_in && yg >= 0 && yg < p.h_glob;   // blur is zero outside the image (cannyEdgeD.cu:142-149)
-      uint4 hb = make_uint4(hq[0], hq[1], hq[2], hq[3]);
-      uint2 fl = make_uint2(f01, f23);
-      if (!in) {
-        hb = make_uint4(0u, 0u, 0u, 0u);
-        fl = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+      uint32_t f01 = __byte_perm(__byte_perm(vv[0], uu[0], 0x5151), __byte_perm(vv[1], uu[1], 0x5151), 0x5410);
+      uint32_t f23 = __byte_perm(__byte_perm(vv[2], uu[2], 0x5151), __byte_perm(vv[3], uu[3], 0x5151), 0x5410);
+      const int yg = yg0 - 2 + br;
+      uint4 *bdst = reinterpret_cast<uint4 *>(smem + FS_BLUR + br * FT_ROWB + lane * 16);
+      uint2 *fdst = reinterpret_cast<uint2 *>(smem + FS_FLAG + br * 256 + lane * 8);
+      if (yg >= 0 && yg < p.h_glob) {   // warp-uniform
+        if (xborder) {                   // CTA-uniform: blur is zero outside the image (cannyEdgeD.cu:142-149)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) hq[j] &= lane_mask;
+          f01 |= ~lane_mask;
+          f23 |= ~lane_mask;
+        }
+        *bdst = make_uint4(hq[0], hq[1], hq[2], hq[3]);
+        *fdst = make_uint2(f01, f23);
+      } else {
+        *bdst = make_uint4(0u, 0u, 0u, 0u);
+        *fdst = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
       }
-      *reinterpret_cast<uint4 *>(smem + FS_BLUR + br * FT_ROWB + lane * 16) = hb;
-      *reinterpret_cast<uint2 *>(smem + FS_FLAG + br * 256 + lane * 8) = fl;
       r0 = r1; r1 = r2; r2 = r3; r3 = r4;
     }
   }
@@ -200,20 +225,23 @@ __global__ void __launch_bounds__(FT_THREADS, 2) k_stencil_fused(const B2cStenci
   // ---- stage 2: exact replay of the S % 159 == 0 pixels (columns 6..249 of the window feed later stages) --------
   {
     const uint4 *ft = reinterpret_cast<const uint4 *>(smem + FS_FLAG);
+    constexpr uint32_t K1 = 0x01010101u, K8 = 0x80808080u;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int i = tid + FT_THREADS * j;
       const uint4 f = ft[i];
-      const uint32_t w[4] = { f.x, f.y, f.z, f.w };
+      const uint32_t z = (((f.x - K1) & ~f.x) | ((f.y - K1) & ~f.y) | ((f.z - K1) & ~f.z) | ((f.w - K1) & ~f.w)) & K8;
+      if (z) {   // some byte of these 16 is zero (a byte above a zero byte may be a false positive: re-checked below)
+        const uint32_t w[4] = { f.x, f.y, f.z, f.w };
+        const int rowcol = ((i >> 4) << 8) | ((i & 15) * 16);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if ((w[q] - 0x01010101u) & ~w[q] & 0x80808080u) {
-          for (int b = 0; b < 4; ++b) {
-            const int col = (i & 15) * 16 + q * 4 + b;
-            if (((w[q] >> (8 * b)) & 0xFFu) == 0u && col >= 6 && col < 250) {
-              const int idx = atomicAdd(cnt, 1);
-              if (idx < FT_LIST_CAP) list[idx] = (uint16_t)(((i >> 4) << 8) | col);
-            }
+        for (int q = 0; q < 4; ++q) {
+          uint32_t zq = (w[q] - K1) & ~w[q] & K8;
+          while (zq) {
+            const int bit = __ffs((int)zq) - 1;
+            zq &= zq - 1u;
+            const int col = (rowcol & 255) + q * 4 + (bit >> 3);
+            if (((w[q] >> (bit - 7)) & 0xFFu) == 0u && col >= 6 && col < 250) list_push(smem, 0, (uint32_t)((rowcol & ~255) | col));
           }
         }
       }
@@ -260,21 +288,35 @@ __global__ void __launch_bounds__(FT_THREADS, 2) k_stencil_fused(const B2cStenci
         const int g = g0 + k;
         if (g < FT_GROWS) {
           dt(g + 2, D2, T2);
-          const int y = Y0 - 1 + g, yg = y + p.y0;
-          const bool in = lane_in && yg >= 0 && yg < p.h_glob;   // grad is zero outside the image (cannyEdgeD.cu:222-229)
-          uint32_t gx[4], gy[4], cand = 0;
+          const int yg = yg0 - 1 + g;
+          uint4 *gxd = reinterpret_cast<uint4 *>(smem + FS_GX + g * FT_ROWB + lane * 16);
+          uint4 *gyd = reinterpret_cast<uint4 *>(smem + FS_GY + g * FT_ROWB + lane * 16);
+          uint8_t *cd = reinterpret_cast<uint8_t *>(smem + FS_CAND) + g * 32 + lane;
+          if (yg >= 0 && yg < p.h_glob) {   // warp-uniform
+            uint32_t gx[4], gy[4], nm = 0u;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            gx[j] = in ? b2c_h2add(b2c_h2fma2(D1[j], D0[j]), D2[j]) : 0u;   // sumX = right - left
-            gy[j] = in ? b2c_h2sub(T0[j], T2[j]) : 0u;                      // sumY = top - bottom
-            const float nl = b2c_fhfma_ll(gx[j], gx[j], b2c_fhfma_ll(gy[j], gy[j], negl));
-            const float nh = b2c_fhfma_hh(gx[j], gx[j], b2c_fhfma_hh(gy[j], gy[j], negl));
-            cand |= (nl >= 0.0f ? 1u : 0u) << (2 * j);
-            cand |= (nh >= 0.0f ? 1u : 0u) << (2 * j + 1);
+            for (int j = 0; j < 4; ++j) {
+              gx[j] = b2c_h2add(b2c_h2fma2(D1[j], D0[j]), D2[j]);   // sumX = right - left
+              gy[j] = b2c_h2sub(T0[j], T2[j]);                      // sumY = top - bottom
+            }
+            if (xborder) {   // CTA-uniform: grad is zero outside the image (cannyEdgeD.cu:222-229)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { gx[j] &= lane_mask; gy[j] &= lane_mask; }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              // sign bit of N - Nlow, shifted into a mask: bit (7-k) set <=> pixel k is NOT a candidate
+              nm = __funnelshift_l(__float_as_uint(b2c_fhfma_ll(gx[j], gx[j], b2c_fhfma_ll(gy[j], gy[j], negl))), nm, 1);
+              nm = __funnelshift_l(__float_as_uint(b2c_fhfma_hh(gx[j], gx[j], b2c_fhfma_hh(gy[j], gy[j], negl))), nm, 1);
+            }
+            *gxd = make_uint4(gx[0], gx[1], gx[2], gx[3]);
+            *gyd = make_uint4(gy[0], gy[1], gy[2], gy[3]);
+            *cd = (uint8_t)~nm;
+          } else {
+            *gxd = make_uint4(0u, 0u, 0u, 0u);
+            *gyd = make_uint4(0u, 0u, 0u, 0u);
+            *cd = 0;
           }
-          *reinterpret_cast<uint4 *>(smem + FS_GX + g * FT_ROWB + lane * 16) = make_uint4(gx[0], gx[1], gx[2], gx[3]);
-          *reinterpret_cast<uint4 *>(smem + FS_GY + g * FT_ROWB + lane * 16) = make_uint4(gy[0], gy[1], gy[2], gy[3]);
-          reinterpret_cast<uint8_t *>(smem + FS_CAND)[g * 32 + lane] = (uint8_t)cand;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             D0[j] = D1[j]; D1[j] = D2[j];
@@ -288,20 +330,15 @@ __global__ void __launch_bounds__(FT_THREADS, 2) k_stencil_fused(const B2cStenci
 
   // ---- stage 3b: candidates of the 240 x 60 output region -> work list -> NMS + double threshold ----------------
   for (int wi = tid; wi < FT_GROWS * 8; wi += FT_THREADS) {
-    const uint32_t w = reinterpret_cast<const uint32_t *>(smem + FS_CAND)[wi];
-    const int g = wi >> 3;
-    if (w != 0u && g >= 1 && g <= FT_Y && Y0 + g - 1 < p.h) {
-      for (int b = 0; b < 4; ++b) {
-        const int ln = (wi & 7) * 4 + b;
-        uint32_t m = (w >> (8 * b)) & 0xFFu;
-        if (ln < 1 || ln > 30) m = 0u;
-        while (m) {
-          const int px = __ffs((int)m) - 1;
-          m &= m - 1u;
-          const int idx = atomicAdd(cnt + 1, 1);
-          if (idx < FT_LIST_CAP) list[idx] = (uint16_t)((g << 8) | (ln * 8 + px));
-        }
-      }
+    uint32_t w = reinterpret_cast<const uint32_t *>(smem + FS_CAND)[wi];   // 4 lanes x 8 pixels, bit (7-k) of a byte = pixel k
+    const int g = wi >> 3, l4 = (wi & 7) * 4;
+    if (l4 == 0) w &= 0xFFFFFF00u;    // lane 0 and lane 31 are halo lanes
+    if (l4 == 28) w &= 0x00FFFFFFu;
+    if (g < 1 || g > FT_Y || Y0 + g - 1 >= p.h) w = 0u;
+    while (w) {
+      const int bit = __ffs((int)w) - 1;
+      w &= w - 1u;
+      list_push(smem, 1, (uint32_t)((g << 8) | ((l4 + (bit >> 3)) * 8 + 7 - (bit & 7))));
     }
   }
   __syncthreads();
@@ -313,17 +350,21 @@ __global__ void __launch_bounds__(FT_THREADS, 2) k_stencil_fused(const B2cStenci
       const uint8_t *cb = reinterpret_cast<const uint8_t *>(smem + FS_CAND);
       for (int i = tid; i < FT_Y * 240; i += FT_THREADS) {
         const int g = 1 + i / 240, col = 8 + i % 240;
-        if (Y0 + g - 1 < p.h && ((cb[g * 32 + (col >> 3)] >> (col & 7)) & 1u)) nms_item(p, smem, g, col);
+        if (Y0 + g - 1 < p.h && ((cb[g * 32 + (col >> 3)] >> (7 - (col & 7))) & 1u)) nms_item(p, smem, g, col);
       }
     }
   }
   __syncthreads();
 
-  // ---- stage 4: the 2-bit map tile -> global --------------------------------------------------------------------
-  for (int i = tid; i < FT_Y * FT_OUTW; i += FT_THREADS) {
-    const int r = i / FT_OUTW, wi = i - r * FT_OUTW;
-    const int y = Y0 + r, gw = blockIdx.x * FT_OUTW + wi;
-    if (y < p.h && gw < p.map_pitch) p.map2[(long long)frame * p.map_frame_stride + (long long)y * p.map_pitch + gw] = s_out[i];
+  // ---- stage 4: the 2-bit map tile -> global (16 threads per row, 15 words) --------------------------------------
+  {
+    const int wi = tid & 15, gw = blockIdx.x * FT_OUTW + wi;
+    uint32_t *dst = p.map2 + (long long)frame * p.map_frame_stride + (long long)Y0 * p.map_pitch + gw;
+    if (wi < FT_OUTW && gw < p.map_pitch) {
+#pragma unroll
+      for (int r = tid >> 4; r < FT_Y; r += FT_THREADS / 16)
+        if (Y0 + r < p.h) dst[(long long)r * p.map_pitch] = s_out[r * FT_OUTW + wi];
+    }
   }
 }
 

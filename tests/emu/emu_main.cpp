@@ -29,6 +29,8 @@ __attribute__((visibility("default"))) int emu_stencil(int impl, const uint8_t *
 {
   B2cStencilParams p;
   memset(&p, 0, sizeof(p));
+  alignas(16) static const uint8_t zeros[256] = { 0 };
+  p.zeros = zeros;
   p.bgr = bgr; p.row_stride = row_stride; p.frame_stride = frame_stride;
   p.w = w; p.h = h; p.y0 = y0; p.h_glob = h_glob; p.nframes = nframes;
   p.map2 = map2; p.map_pitch = (w + 15) / 16; p.map_frame_stride = (long long)h * p.map_pitch;
