@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -209,9 +210,11 @@ void fill_stencil_params(b2c_ctx *c, B2cStencilParams &p, const uint8_t *bgr, si
   fill_gk(p.gk);
   for (int k = 0; k < 3; ++k) {
     const float a = (float)(256 * k + c->lo + 1), b = (float)(256 * k + c->hi + 1);
-    p.n_lo[k] = 4.0f * a * a;   // exact: < 2^24
-    p.n_hi[k] = 4.0f * b * b;
+    p.n_lo[k] = ldexpf(4.0f * a * a, -48);   // exact: < 2^24
+    p.n_hi[k] = ldexpf(4.0f * b * b, -48);   // fused kernel: sums carry the fp16-subnormal scale 2^-24
   }
+  p.n_wrap[0] = ldexpf(262144.0f, -48);    // 4*256^2
+  p.n_wrap[1] = ldexpf(1048576.0f, -48);   // 4*512^2
   p.pitch8 = c->pitch8;
   p.pitchf = c->pitchf;
 }

@@ -49,7 +49,8 @@ struct B2cStencilParams {
   // double threshold in the N = sumX^2+sumY^2 domain.  The reference thresholds v = (unsigned char)grad
   // (cannyEdgeD.cu:267,290), grad = 0.5*sqrt(N); the cast wraps mod 256, and trunc(grad) >= m <=> N >= 4m^2, so
   //   v > T  <=>  N in [n[0], 4*256^2) or [n[1], 4*512^2) or [n[2], inf),  n[k] = 4*(256k + T + 1)^2
-  float n_lo[3], n_hi[3];
+  // The fused kernel works on fp16-subnormal-scaled sums (x 2^-24), so its N is scaled by 2^-48: n_scale.
+  float n_lo[3], n_hi[3], n_wrap[2];
   // optional per-stage outputs (frame 0 only; null = not written)
   uint8_t *mono, *blur, *nms, *thresh;
   float *grad;

@@ -25,7 +25,11 @@
 
 namespace b2c
 {
-constexpr int FT_X = 240, FT_Y = 60, FT_THREADS = 256, FT_WARPS = 8;
+#ifndef B2C_FT_Y
+#define B2C_FT_Y 36
+#endif
+constexpr int FT_X = 240, FT_Y = B2C_FT_Y, FT_THREADS = 256, FT_WARPS = 8;
+constexpr int FT_CTAS_PER_SM = FT_Y <= 36 ? 3 : 2;
 constexpr int FT_MROWS = FT_Y + 8;   // gray rows   Y0-4 .. Y0+63
 constexpr int FT_BROWS = FT_Y + 4;   // blur rows   Y0-2 .. Y0+61
 constexpr int FT_GROWS = FT_Y + 2;   // gx/gy rows  Y0-1 .. Y0+60
@@ -33,15 +37,18 @@ constexpr int FT_ROWB = 512;         // bytes per tile row: 256 columns x 16 bit
 constexpr int FT_OUTW = FT_X / 16;   // map words per tile row
 // shared-memory map (bytes).  gx/gy alias gray + flags (dead once the Gaussian is final).
 constexpr int FS_MONO = 0;
-constexpr int FS_FLAG = FS_MONO + FT_MROWS * FT_ROWB;   // 64 rows x 256 B: byte == 0 <=> S % 159 == 0
+constexpr int FS_FLAG = FS_MONO + FT_MROWS * FT_ROWB;   // blur rows x 256 B: byte == 0 <=> S % 159 == 0
+constexpr int FT_R1 = FT_BROWS / FT_WARPS;                    // blur rows per warp
+constexpr int FT_R3 = (FT_GROWS + FT_WARPS - 1) / FT_WARPS;   // gx/gy rows per warp
+static_assert(FT_BROWS % FT_WARPS == 0, "blur rows must split evenly over the warps");
 constexpr int FS_GX = 0;
 constexpr int FS_GY = FT_GROWS * FT_ROWB;
 constexpr int FS_A_END = 2 * FT_GROWS * FT_ROWB;
 static_assert(FS_A_END >= FS_FLAG + FT_BROWS * 256, "alias region too small");
 constexpr int FS_BLUR = FS_A_END;
 constexpr int FS_CAND = FS_BLUR + FT_BROWS * FT_ROWB;   // 62 rows x 32 lanes, 1 byte = 8 candidate bits
-constexpr int FS_OUT = FS_CAND + 2048;                  // 60 x 15 map words
-constexpr int FS_LIST = FS_OUT + 3840;
+constexpr int FS_OUT = FS_CAND + ((FT_GROWS * 32 + 127) / 128) * 128;   // FT_Y x 15 map words
+constexpr int FS_LIST = FS_OUT + ((FT_Y * FT_OUTW * 4 + 127) / 128) * 128;
 constexpr int FT_LIST_CAP = 2048;
 constexpr int FS_CNT = FS_LIST + FT_LIST_CAP * 2;
 constexpr int FUSED_SMEM = FS_CNT + 16;
@@ -68,7 +75,7 @@ __device__ __forceinline__ void gauss_replay(const B2cStencilParams &p, char *sm
   for (int r = 0; r < 5; ++r)
 #pragma unroll
     for (int c = 0; c < 5; ++c) f = __fmaf_rn(p.gk[r * 5 + c], (float)M[r * 256 + c], f);
-  reinterpret_cast<uint16_t *>(smem + FS_BLUR)[br * 256 + col] = (uint16_t)b2c_u2h_bits((unsigned)f);
+  reinterpret_cast<uint16_t *>(smem + FS_BLUR)[br * 256 + col] = (uint16_t)(unsigned)f;   // fp16 subnormal = the integer itself
 }
 
 // Direction, non-maximum suppression and double threshold for one candidate pixel (src/cvp/cannyEdgeD.cu:196,
@@ -87,8 +94,14 @@ __device__ __forceinline__ void nms_item(const B2cStencilParams &p, char *smem, 
   const uint32_t qx = GX[i + o], qy = GY[i + o], rx = GX[i - o], ry = GY[i - o];
   const float nq = b2c_fhfma_ll(qx, qx, b2c_fhfma_ll(qy, qy, 0.0f)), nr = b2c_fhfma_ll(rx, rx, b2c_fhfma_ll(ry, ry, 0.0f));
   if (nq > n || nr > n) return;
-  const bool strong = (n >= p.n_hi[0] && n < 262144.0f) || (n >= p.n_hi[1] && n < 1048576.0f) || n >= p.n_hi[2];
-  const bool weak = !strong && ((n >= p.n_lo[0] && n < 262144.0f) || (n >= p.n_lo[1] && n < 1048576.0f) || n >= p.n_lo[2]);
+  bool strong, weak;
+  if (n < p.n_wrap[0]) {   // trunc(grad) < 256: no wrap of the (unsigned char) cast; n >= n_lo[0] is what made it a candidate
+    strong = n >= p.n_hi[0];
+    weak = !strong;
+  } else {
+    strong = (n >= p.n_hi[1] && n < p.n_wrap[1]) || n >= p.n_hi[2];
+    weak = !strong && ((n >= p.n_lo[1] && n < p.n_wrap[1]) || n >= p.n_lo[2]);
+  }
   if (strong || weak) {
     const int c = col - 8;
     atomicOr(reinterpret_cast<uint32_t *>(smem + FS_OUT) + (g - 1) * FT_OUTW + (c >> 4), (strong ? 1u : 0x10000u) << (c & 15));
@@ -107,7 +120,7 @@ __device__ __forceinline__ void list_push(char *smem, int which, uint32_t item)
   if (idx < FT_LIST_CAP) reinterpret_cast<uint16_t *>(smem + FS_LIST)[idx] = (uint16_t)item;
 }
 
-__global__ void __launch_bounds__(FT_THREADS, 2) k_stencil_fused(const B2cStencilParams p)
+__global__ void __launch_bounds__(FT_THREADS, FT_CTAS_PER_SM) k_stencil_fused(const B2cStencilParams p)
 {
   B2C_DYN_SMEM(smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -161,10 +174,10 @@ __global__ void __launch_bounds__(FT_THREADS, 2) k_stencil_fused(const B2cStenci
   // S = sum k*gray (exact, <= 40545) per 16-bit lane; q = S/159 via multiply-high; blur = q unless S%159 == 0.
   {
     const uint4 *mt = reinterpret_cast<const uint4 *>(smem + FS_MONO) + lane;
-    const int b0 = warp * 8;
+    const int b0 = warp * FT_R1;
     uint4 r0 = mt[(b0 + 0) * 32], r1 = mt[(b0 + 1) * 32], r2 = mt[(b0 + 2) * 32], r3 = mt[(b0 + 3) * 32];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < FT_R1; ++k) {
       const int br = b0 + k;
       const uint4 r4 = mt[(br + 4) * 32];
       const uint32_t a0[4] = { r0.x, r0.y, r0.z, r0.w }, a1[4] = { r1.x, r1.y, r1.z, r1.w }, a2[4] = { r2.x, r2.y, r2.z, r2.w },
@@ -192,12 +205,14 @@ __global__ void __launch_bounds__(FT_THREADS, 2) k_stencil_fused(const B2cStenci
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t S = (v0[j] + v0[j + 2] + v2[j]) + (o1[j] + o1[j + 1]);
-        // upper 16 bits of the product = lane / 159; byte 1 == 0 <=> lane % 159 == 0; +0x6400 in the top = fp16 bias 1024
-        const uint32_t U = __umulhi(S, 27012373u) + 0x64000000u;         // high lane (low lane adds < 1/159)
-        const uint32_t V = __umulhi(S << 16, 27012373u) + 0x64000000u;   // low lane
+        // upper 16 bits of the product = lane / 159; byte 1 == 0 <=> lane % 159 == 0
+        const uint32_t U = __umulhi(S, 27012373u);         // high lane (the low lane adds < 1/159)
+        const uint32_t V = __umulhi(S << 16, 27012373u);   // low lane
         uu[j] = U;
         vv[j] = V;
-        hq[j] = b2c_h2sub(__byte_perm(V, U, 0x7632), 0x64006400u);       // (q_lo, q_hi) as exact fp16
+        // (q_lo, q_hi) as 16-bit integers == fp16 SUBNORMALS q * 2^-24: every later fp16 value is an integer
+        // multiple of 2^-24 below 2^-14, so the fp16x2 arithmetic stays exact and needs no int->half conversion
+        hq[j] = __byte_perm(V, U, 0x7632);
       }
       uint32_t f01 = __byte_perm(__byte_perm(vv[0], uu[0], 0x5151), __byte_perm(vv[1], uu[1], 0x5151), 0x5410);
       uint32_t f23 = __byte_perm(__byte_perm(vv[2], uu[2], 0x5151), __byte_perm(vv[3], uu[3], 0x5151), 0x5410);
@@ -227,22 +242,23 @@ __global__ void __launch_bounds__(FT_THREADS, 2) k_stencil_fused(const B2cStenci
     const uint4 *ft = reinterpret_cast<const uint4 *>(smem + FS_FLAG);
     constexpr uint32_t K1 = 0x01010101u, K8 = 0x80808080u;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < (FT_BROWS * 16 + FT_THREADS - 1) / FT_THREADS; ++j) {
       const int i = tid + FT_THREADS * j;
+      if (i >= FT_BROWS * 16) break;
       const uint4 f = ft[i];
       const uint32_t z = (((f.x - K1) & ~f.x) | ((f.y - K1) & ~f.y) | ((f.z - K1) & ~f.z) | ((f.w - K1) & ~f.w)) & K8;
       if (z) {   // some byte of these 16 is zero (a byte above a zero byte may be a false positive: re-checked below)
         const uint32_t w[4] = { f.x, f.y, f.z, f.w };
-        const int rowcol = ((i >> 4) << 8) | ((i & 15) * 16);
+        uint32_t m16 = 0u;   // bit (4q+b) <=> byte b of word q looks zero
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t zq = (w[q] - K1) & ~w[q] & K8;
-          while (zq) {
-            const int bit = __ffs((int)zq) - 1;
-            zq &= zq - 1u;
-            const int col = (rowcol & 255) + q * 4 + (bit >> 3);
-            if (((w[q] >> (bit - 7)) & 0xFFu) == 0u && col >= 6 && col < 250) list_push(smem, 0, (uint32_t)((rowcol & ~255) | col));
-          }
+        for (int q = 0; q < 4; ++q) m16 |= (((((w[q] - K1) & ~w[q] & K8) >> 7) * 0x00204081u) >> 21 & 0xFu) << (4 * q);
+        const int row8 = (i >> 4) << 8, col0 = (i & 15) * 16;
+        const uint8_t *fb = reinterpret_cast<const uint8_t *>(ft + i);
+        while (m16) {
+          const int k = __ffs((int)m16) - 1;
+          m16 &= m16 - 1u;
+          const int col = col0 + k;
+          if (fb[k] == 0 && col >= 6 && col < 250) list_push(smem, 0, (uint32_t)(row8 | col));
         }
       }
     }
@@ -265,7 +281,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2) k_stencil_fused(const B2cStenci
   // ---- stage 3a: Sobel sums in exact fp16x2, rows Y0-1 .. Y0+60; N >= low threshold -> candidate bit -------------
   {
     const uint4 *bt = reinterpret_cast<const uint4 *>(smem + FS_BLUR) + lane;
-    const int g0 = warp * 8;
+    const int g0 = warp * FT_R3;
     uint32_t D0[4], T0[4], D1[4], T1[4], D2[4], T2[4];
     const float negl = -p.n_lo[0];
     auto dt = [&](int row, uint32_t (&D)[4], uint32_t (&T)[4]) {
@@ -284,7 +300,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2) k_stencil_fused(const B2cStenci
       dt(g0, D0, T0);
       dt(g0 + 1, D1, T1);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
+      for (int k = 0; k < FT_R3; ++k) {
         const int g = g0 + k;
         if (g < FT_GROWS) {
           dt(g + 2, D2, T2);

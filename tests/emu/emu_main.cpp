@@ -38,9 +38,11 @@ __attribute__((visibility("default"))) int emu_stencil(int impl, const uint8_t *
   fill_gk(p.gk);
   for (int k = 0; k < 3; ++k) {
     const float a = (float)(256 * k + lo + 1), b = (float)(256 * k + hi + 1);
-    p.n_lo[k] = 4.0f * a * a;
-    p.n_hi[k] = 4.0f * b * b;
+    p.n_lo[k] = ldexpf(4.0f * a * a, -48);
+    p.n_hi[k] = ldexpf(4.0f * b * b, -48);   // fused kernel: sums carry the fp16-subnormal scale 2^-24
   }
+  p.n_wrap[0] = ldexpf(262144.0f, -48);
+  p.n_wrap[1] = ldexpf(1048576.0f, -48);
   p.mono = mono; p.blur = blur; p.grad = grad; p.nms = nms; p.thresh = thresh;
   p.pitch8 = w; p.pitchf = w;
   if (impl == 1) {
