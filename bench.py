@@ -37,6 +37,11 @@ WORKLOADS = {
     "batch1080p": dict(w=1920, h=1080, n=64, desc="64 x 1920x1080 BGR8 synthetic 'scene' frames per GPU, device-resident (BASELINE configs[1])"),
     "frame4k": dict(w=3840, h=2160, n=1, desc="one 3840x2160 BGR8 synthetic 'scene' frame, device-resident (BASELINE configs[2])"),
     "frame720p": dict(w=1280, h=720, n=1, desc="one 1280x720 BGR8 synthetic 'scene' frame (BASELINE configs[0])"),
+    # strong-scaling workloads (total work fixed as N grows); not the default bench line
+    "streams1080p": dict(w=1920, h=1080, n=64, chunks_total=32, desc="8 independent 1920x1080 streams x 256 frames = 32 chunks of 64 device-resident frames, "
+                         "stream s on GPU s mod N, no collective (BASELINE configs[3])"),
+    "giga": dict(w=16384, h=16384, n=1, desc="one 16384x16384 BGR8 synthetic mosaic, row bands over the ranks, 4-row input halo exchange + cross-band hysteresis "
+                 "to a global fixpoint (BASELINE configs[4])"),
 }
 
 
@@ -196,7 +201,13 @@ def run_ours(args, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w, h, n = wl["w"], wl["h"], wl["n"]
-    px_per_step = n * w * h
+    reps = 1
+    if "chunks_total" in wl:
+        if wl["chunks_total"] % world:
+            raise SystemExit(f"{args.workload}: {wl['chunks_total']} chunks do not split over {world} ranks")
+        reps = wl["chunks_total"] // world
+    px_per_chunk = n * w * h
+    px_per_step = px_per_chunk * reps
 
     # synthetic frames: stream id = rank, so every GPU works on different pictures
     distinct = min(n, 16)
@@ -240,6 +251,9 @@ def run_ours(args, wl):
         b.record()
         hyst()
         e.record()
+        for _ in range(reps - 1):
+            stencil()
+            hyst()
     barrier()
     clocks = sampler.stop()
     launches = c.launches - l0
@@ -256,13 +270,14 @@ def run_ours(args, wl):
     # ---- e2e: pinned host frames -> b2c_run_batch_host -> host edge maps (H2D + D2H inside the timed region) ----
     pin_in, pin_out = _lib._vp(), _lib._vp()
     _lib.check(lib.b2c_host_alloc(host.nbytes, pin_in))
-    _lib.check(lib.b2c_host_alloc(px_per_step, pin_out))
+    _lib.check(lib.b2c_host_alloc(px_per_chunk, pin_out))
     import ctypes as C
     C.memmove(pin_in.value, host.ctypes.data, host.nbytes)
     e2e_steps = max(3, min(args.steps, 20))
 
     def e2e_step():
-        _lib.check(lib.b2c_run_batch_host(H, pin_in.value, row_stride, n, pin_out.value, 0), H, "run_batch_host")
+        for _ in range(reps):
+            _lib.check(lib.b2c_run_batch_host(H, pin_in.value, row_stride, n, pin_out.value, 0), H, "run_batch_host")
 
     for _ in range(2):
         e2e_step()
@@ -283,7 +298,7 @@ def run_ours(args, wl):
     if rank == 0:
         peak, which = peaks()
         k_ms = statistics.mean(stencil_ms)
-        achieved = px_per_step * STENCIL_BYTES_PER_PX / (k_ms * 1e-3) / 1e9
+        achieved = px_per_chunk * STENCIL_BYTES_PER_PX / (k_ms * 1e-3) / 1e9
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "stencil_traffic.json"))).get("bytes_per_launch_" + args.workload)
@@ -291,14 +306,14 @@ def run_ours(args, wl):
             pass
         line = {
             "metric": "Canny edge-map throughput (fused stencil + on-device hysteresis)", "value": value, "unit": "Mpixel/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if "chunks_total" in wl else "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": wl["desc"], "frames_per_gpu": n, "width": w, "height": h, "thresholds": [10, 40],
-                       "l2_policy": "inputs (%.0f MB/step/GPU) larger than the 126 MB L2, no flush" % (px_per_step * 3 / 1e6) if px_per_step * 3 > 130e6 else "input smaller than L2: latency workload, L2-warm",
+                       "l2_policy": "inputs (%.0f MB/launch/GPU) larger than the 126 MB L2, no flush" % (px_per_chunk * 3 / 1e6) if px_per_chunk * 3 > 130e6 else "input smaller than L2: latency workload, L2-warm",
                        "parallelism": f"frame-parallel x{world}, no collective", "stencil_impl": c.info("stencil_impl"),
                        "e2e_equals_device_path": same, "edge_pixel_fraction": edge_frac},
             "roofline": {"bound": "hbm", "kernel": "fused stencil (BGR8 -> 2-bit weak/strong map)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": which, "algorithmic_bytes_per_launch": px_per_step * STENCIL_BYTES_PER_PX,
+                         "traffic": traffic, "peak_source": which, "algorithmic_bytes_per_launch": px_per_chunk * STENCIL_BYTES_PER_PX,
                          "kernel_ms": k_ms, "hysteresis_ms": statistics.mean(hyst_ms), "stencil_share_of_step": sum(stencil_ms) / (sum(stencil_ms) + sum(hyst_ms))},
             "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": px_per_step * 3, "d2h_bytes_per_step": px_per_step, "steps": e2e_steps,
                     "api": "b2c_run_batch_host (pinned host frames in, host u8 edge maps out)"},
@@ -318,6 +333,85 @@ def run_ours(args, wl):
         dist.destroy_process_group()
 
 
+def run_giga(args, wl):
+    """BASELINE configs[4]: one 16384x16384 image, one row band per rank (strong scaling).  A step = 4-row input halo
+    exchange with the neighbour ranks (NCCL send/recv), fused stencil on the band, then band-local hysteresis +
+    boundary-row exchange + convergence all-reduce until the global fixpoint, and the u8 expansion."""
+    import torch
+    import torch.distributed as dist
+    from cudacam_b200 import bands, synth
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the Canny path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W, Hh = wl["w"], wl["h"]
+    y0, rows = bands.band_rows(Hh, world, rank)
+    band_host = synth.giga_rows(y0, y0 + rows, W, Hh)
+    be = bands.CudaBandBackend(W, rows, y0, Hh, device=local)
+    be.load(band_host)
+    bc = bands.BandCanny(be, rank, world, dist if world > 1 else None)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        bc.run()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    rounds = 0
+    for _ in range(args.steps):
+        rounds = bc.run()
+    b.record()
+    barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([a.elapsed_time(b)], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    # e2e: band from host memory, edge map back to host, every step
+    e2e_steps = min(args.steps, 3)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        be.load(band_host)
+        bc.run()
+        edges = be.edges()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        peak, which = peaks()
+        px = W * Hh
+        line = {
+            "metric": "Canny edge-map throughput (row-band sharded gigapixel image)", "value": px * args.steps / (total_ms * 1e-3) / 1e6, "unit": "Mpixel/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": wl["desc"], "width": W, "height": Hh, "band_rows_rank0": rows, "thresholds": [10, 40], "global_hysteresis_rounds": rounds,
+                       "l2_policy": "band input (%.0f MB) larger than the 126 MB L2, no flush" % (rows * W * 3 / 1e6), "parallelism": f"row bands x{world}, NCCL halo + boundary rows + 1-int all-reduce per round",
+                       "edge_pixel_fraction_rank0": float((edges == 255).mean())},
+            "roofline": {"bound": "hbm", "kernel": "whole step (4 B/pixel end to end: 3 in + 1 out)", "achieved": px * 4.0 / (total_ms / args.steps * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s",
+                         "frac": px * 4.0 / (total_ms / args.steps * 1e-3) / 1e9 / world / peak, "traffic": None, "peak_source": which},
+            "e2e": {"value": px * e2e_steps / float(t.item()) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": px * 3, "d2h_bytes_per_step": px, "steps": e2e_steps,
+                    "api": "CudaBandBackend.load (pageable host band) + BandCanny.run + edges() download"},
+            "gpu_launches": None, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    be.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -332,6 +426,8 @@ def main():
         if args.steps > 10:
             args.steps = 10   # bounded: the reference needs ~1 ms per frame
         run_reference(args, wl)
+    elif args.workload == "giga":
+        run_giga(args, wl)
     else:
         run_ours(args, wl)
 

@@ -30,3 +30,24 @@ def batch(kind, n, w, h, stream=0, distinct=None):
     for f in range(distinct, n):
         out[f] = out[f % distinct]
     return out
+
+
+_GIGA_TILE = 4096
+
+
+def giga_rows(y0, y1, w=16384, h=16384):
+    """Rows [y0, y1) of the synthetic gigapixel image of BASELINE config 5: a mosaic of four distinct 4096x4096
+    'scene' tiles (tile (ty, tx) uses picture (ty + tx) % 4), cropped to w x h.  Returns (y1-y0, w, 3) uint8."""
+    T = _GIGA_TILE
+    tiles = {}
+    out = np.empty((y1 - y0, w, 3), np.uint8)
+    for y in range(y0, y1):
+        ty, ry = divmod(y, T)
+        for tx in range((w + T - 1) // T):
+            k = (ty + tx) % 4
+            if k not in tiles:
+                tiles[k] = frame("scene", stream_seed(1000, k), T, T)
+            x0 = tx * T
+            n = min(T, w - x0)
+            out[y - y0, x0:x0 + n] = tiles[k][ry, :n]
+    return out

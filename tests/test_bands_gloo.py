@@ -1,0 +1,175 @@
+"""Row-band sharding on the CPU: world_size 2 and 3 over gloo, kernels through the emulator (tests/emu), compared
+with the oracle on the whole image.  Covers the host logic of cudacam_b200/bands.py (halo exchange of 4 input rows,
+boundary-row exchange of the edge bit-plane, convergence all-reduce) without a GPU; the NCCL/GPU twin of this test
+is tests/test_gpu_multi.py."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import emu_py as E
+import oracle_py as O
+from cudacam_b200 import bands, synth
+
+
+class EmuBandBackend:
+    """Same interface as bands.CudaBandBackend; pixel work by the emulated kernels (test-only)."""
+
+    def __init__(self, width, rows, y0, height_global, thresh_override=None):
+        self.width, self.rows, self.y0, self.height_global = width, rows, y0, height_global
+        self.row_stride = (width * 3 + 15) // 16 * 16
+        self.buf = torch.zeros((rows + 2 * bands.HALO, self.row_stride), dtype=torch.uint8)
+        self.wpr = (width + 31) // 32
+        self._b = [torch.zeros(self.wpr, dtype=torch.int32) for _ in range(2)]
+        self._g = [torch.zeros(self.wpr, dtype=torch.int32) for _ in range(2)]
+        self._edges = None
+        self._map2 = None
+        self._override = thresh_override   # (rows, w) u8 {0,128,255}: skips the stencil (hysteresis-only tests)
+
+    def input_rows(self, r0, r1):
+        return self.buf[r0:r1]
+
+    def load(self, band_host):
+        t = torch.from_numpy(np.ascontiguousarray(band_host).reshape(self.rows, self.width * 3))
+        self.buf[bands.HALO:bands.HALO + self.rows, :self.width * 3] = t
+
+    def stencil(self):
+        if self._override is not None:
+            self._map2 = O.thresh_to_map2(self._override)
+            return
+        impl = 0 if self.width % 8 == 0 else 1
+        a = self.buf.numpy()
+        if impl == 0:
+            self._map2 = E.stencil_raw(a, bands.HALO, self.width, self.rows, impl=0, y0=self.y0, h_glob=self.height_global)
+        else:
+            f = np.ascontiguousarray(a[:, :self.width * 3]).reshape(a.shape[0], self.width, 3)
+            self._map2 = E.stencil(f, impl=1, y0=self.y0, h_glob=self.height_global, rows=self.rows, row0=bands.HALO)["map2"][0]
+
+    def hysteresis(self, first, write_edges):
+        # the emulator entry rebuilds the planes from the 2-bit map on every call; with the ghost rows as extra
+        # seeds that reaches the same fixpoint as the product's re-entry on the retained planes
+        gt = self._g[0].numpy().view(np.uint32)
+        gb = self._g[1].numpy().view(np.uint32)
+        edges, bits, _, _ = E.hysteresis(self._map2, self.width, grid_blocks=2, tile_rows=0, ghost_top=gt, ghost_bot=gb)
+        self._edges = edges[0]
+        self._b[0].copy_(torch.from_numpy(bits[0][0].view(np.int32).copy()))
+        self._b[1].copy_(torch.from_numpy(bits[0][-1].view(np.int32).copy()))
+
+    def sync(self):
+        pass
+
+    def boundary(self, which):
+        return self._b[which]
+
+    def ghost(self, which):
+        return self._g[which]
+
+    def edges(self):
+        return self._edges
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, mode, w, h, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        y0, rows = bands.band_rows(h, world, rank)
+        if mode == "image":
+            img = synth.frame("scene", 31, w, h)
+            be = EmuBandBackend(w, rows, y0, h)
+            be.load(img[y0:y0 + rows])
+        else:
+            t = _snake_map(w, h)
+            be = EmuBandBackend(w, rows, y0, h, thresh_override=t[y0:y0 + rows])
+        bc = bands.BandCanny(be, rank, world, dist)
+        rounds = bc.run()
+        q.put((rank, y0, rows, rounds, be.edges().copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def _snake_map(w, h):
+    """A weak chain that crosses every seam several times, seeded by ONE strong pixel in the top band, plus weak
+    islands that must vanish: needs several global rounds."""
+    t = np.zeros((h, w), np.uint8)
+    x = 2
+    up = False
+    while x + 6 < w:
+        t[2:h - 2, x] = 128           # full-height vertical stroke
+        if up:
+            t[2, x:x + 6] = 128       # connect at the top
+        else:
+            t[h - 3, x:x + 6] = 128   # connect at the bottom
+        up = not up
+        x += 6
+    t[2, 2] = 255
+    t[h // 2, w - 2] = 128            # isolated
+    return t
+
+
+def _run(world, mode, w, h):
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, mode, w, h, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get() for _ in range(world)]
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    out = np.zeros((h, w), np.uint8)
+    for rank, y0, rows, rounds, e in res:
+        out[y0:y0 + rows] = e
+    return out, max(r[3] for r in res)
+
+
+def test_band_rows_partition():
+    for h, world in ((16384, 8), (1080, 7), (10, 3), (5, 5)):
+        spans = [bands.band_rows(h, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and sum(s[1] for s in spans) == h
+        for a, b in zip(spans, spans[1:]):
+            assert a[0] + a[1] == b[0]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_image_equals_unsharded(world):
+    w, h = 96, 60
+    got, rounds = _run(world, "image", w, h)
+    want = O.canny(synth.frame("scene", 31, w, h))["edges"]
+    assert np.array_equal(got, want)
+    assert rounds >= 1
+
+
+def test_cross_band_hysteresis_needs_several_rounds():
+    w, h = 64, 36
+    got, rounds = _run(2, "snake", w, h)
+    want = O.hysteresis(_snake_map(w, h))
+    assert np.array_equal(got, want)
+    assert want[h - 3, w - 10] == 255 or want.sum() > 0
+    assert got[h // 2, w - 2] == 0
+    assert rounds >= 3, rounds
+
+
+def test_run_local_single_process_bands():
+    """The single-process driver (bands.run_local) follows the same protocol: 3 bands of unequal height."""
+    w, h = 64, 37
+    t = _snake_map(w, h)
+    bes = []
+    for r in range(3):
+        y0, rows = bands.band_rows(h, 3, r)
+        bes.append(EmuBandBackend(w, rows, y0, h, thresh_override=t[y0:y0 + rows]))
+    rounds = bands.run_local(bes)
+    got = np.concatenate([b.edges() for b in bes])
+    assert np.array_equal(got, O.hysteresis(t)) and rounds >= 3

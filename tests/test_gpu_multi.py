@@ -1,0 +1,105 @@
+"""GPU tests of the two partitioned modes: row bands of one image (bit-identical to the unsharded
+run) and frame-parallel handles on several devices.  The single-GPU cases run everywhere; the NCCL cases need >= 2
+GPUs (`gpurun --gpus 2`) and skip otherwise."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import oracle_py as O
+import cudacam_b200 as cb
+from cudacam_b200 import _lib, bands, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _ndev():
+    return _lib.lib.b2c_device_count()
+
+
+def _unsharded(img):
+    h, w, _ = img.shape
+    with cb.CannyEdge(w, h) as c:
+        c.run(img)
+        return c.edges()
+
+
+@pytest.mark.parametrize("kind,w,h,nb", [("scene", 1920, 1000, 3), ("steps", 640, 203, 5), ("noise", 328, 64, 2), ("scene", 4096, 4096, 4)])
+def test_local_bands_equal_unsharded(kind, w, h, nb):
+    """nb bands driven from one process (all on cuda:0, or spread over the devices present)."""
+    img = synth.frame(kind, 11, w, h)
+    want = _unsharded(img)
+    if h <= 1100:
+        assert np.array_equal(want, O.canny(img)["edges"])
+    nd = max(1, _ndev())
+    bes = []
+    for r in range(nb):
+        y0, rows = bands.band_rows(h, nb, r)
+        b = bands.CudaBandBackend(w, rows, y0, h, device=r % nd)
+        b.load(img[y0:y0 + rows])
+        bes.append(b)
+    rounds = bands.run_local(bes)
+    got = np.concatenate([b.edges() for b in bes])
+    for b in bes:
+        b.close()
+    assert rounds >= 1
+    assert np.array_equal(got, want)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _nccl_worker(rank, world, port, w, h, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        img = synth.frame("scene", 13, w, h)
+        y0, rows = bands.band_rows(h, world, rank)
+        be = bands.CudaBandBackend(w, rows, y0, h, device=rank)
+        be.load(img[y0:y0 + rows])
+        rounds = bands.BandCanny(be, rank, world, dist).run()
+        q.put((rank, y0, rows, rounds, be.edges()))
+        be.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_nccl_bands_equal_unsharded(world):
+    if _ndev() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    w, h = 2048, 1536
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, w, h, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get() for _ in range(world)]
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    got = np.zeros((h, w), np.uint8)
+    for rank, y0, rows, rounds, e in res:
+        got[y0:y0 + rows] = e
+    assert np.array_equal(got, _unsharded(synth.frame("scene", 13, w, h)))
+
+
+def test_frame_parallel_handles_on_every_device():
+    """One independent handle per GPU, no shared state (frame batches split with no collective)."""
+    w, h, n = 640, 360, 6
+    frames = synth.batch("scene", n, w, h)
+    want = np.stack([O.canny(frames[i])["edges"] for i in range(n)])
+    for dev in range(max(1, _ndev())):
+        with cb.CannyEdge(w, h, device=dev, max_batch=4) as c:
+            assert np.array_equal(c.run_batch(frames), want), dev
