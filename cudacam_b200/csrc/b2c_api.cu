@@ -24,6 +24,7 @@
 #include "k_hysteresis.cuh"
 #include "k_hysteresis_uf.cuh"
 #include "k_stencil_fused.cuh"
+#include "k_stencil_march.cuh"
 #include "k_stencil_tile.cuh"
 #include "k_views.cuh"
 
@@ -42,7 +43,7 @@ struct b2c_ctx {
   int sm_count = 0;
   uint8_t lo = 10, hi = 40;   // src/cvp/cannyEdgeH.cu:22-23
   bool profiling = true;      // src/cvp/cannyEdgeH.cu:24
-  int stencil_impl = 0;       // 0 fused, 1 tile
+  int stencil_impl = 0;       // 0 marching warp-per-strip kernel, 1 staged tile kernel, 2 fused CTA-tile kernel
   int hyst_impl = 0;          // 0 union-find (constant number of phases), 1 tile rounds
   int hyst_tile_rows = 16;
   int hyst_max_rounds = 1 << 20;
@@ -187,6 +188,7 @@ int alloc_common(b2c_ctx *c)
   c->uf_grid = c->sm_count * per_sm;
   CK(c, cudaFuncSetAttribute(b2c::k_stencil_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2c::TILE_SMEM));
   CK(c, cudaFuncSetAttribute(b2c::k_stencil_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2c::TILE_SMEM));
+  if (b2c::march_configure() != cudaSuccess) return set_err(c, cudaGetLastError(), "march_configure");
   return b2c::fused_configure() == cudaSuccess ? B2C_OK : set_err(c, cudaGetLastError(), "fused_configure");
 }
 
@@ -224,7 +226,10 @@ int launch_stencil(b2c_ctx *c, const uint8_t *bgr, size_t row_stride, size_t fra
 {
   B2cStencilParams p;
   fill_stencil_params(c, p, bgr, row_stride, frame_stride, n);
-  if (c->stencil_impl == 0 && b2c::fused_supported(p)) {
+  if (c->stencil_impl == 0 && b2c::march_supported(p)) {
+    cudaError_t e = b2c::march_launch(p, c->sm_count, st);
+    if (e != cudaSuccess) return set_err(c, e, "k_stencil_march launch");
+  } else if (c->stencil_impl == 2 && b2c::fused_supported(p)) {
     cudaError_t e = b2c::fused_launch(p, c->sm_count, st);
     if (e != cudaSuccess) return set_err(c, e, "k_stencil_fused launch");
   } else {
@@ -863,7 +868,7 @@ int b2c_set_option(b2c_handle c, const char *name, int value)
 {
   if (!c || !name) return B2C_ERR_INVALID;
   if (!strcmp(name, "stencil_impl")) {
-    if (value < 0 || value > 1) return B2C_ERR_INVALID;
+    if (value < 0 || value > 2) return B2C_ERR_INVALID;
     c->stencil_impl = value;
     return B2C_OK;
   }

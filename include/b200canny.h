@@ -142,7 +142,8 @@ B2C_API const char *b2c_version(void);
 B2C_API int b2c_device_count(void);
 /* kernels launched by this handle since creation (bench.py reports it as gpu_launches) */
 B2C_API long long b2c_launch_count(b2c_handle h);
-/* choose the stencil implementation: 0 = fused register-marching kernel (default), 1 = staged tile kernel */
+/* options: "stencil_impl" 0 = marching warp-per-strip kernel (default), 1 = staged tile kernel (all-stages path),
+ * 2 = fused CTA-tile kernel; "hyst_impl" 0 = union-find (default), 1 = tile rounds; "hyst_max_rounds" */
 B2C_API int b2c_set_option(b2c_handle h, const char *name, int value);
 /* read-only facts: "hyst_rounds" (rounds used by the last b2c_run), "hyst_grid", "sm_count", "stencil_impl",
  * "in_row_stride", "plane_pitch_words", "map_pitch_words" */

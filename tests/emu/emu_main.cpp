@@ -10,6 +10,7 @@
 #include "../../cudacam_b200/csrc/k_stencil_tile.cuh"
 #ifdef B2C_EMU_FUSED
 #include "../../cudacam_b200/csrc/k_stencil_fused.cuh"
+#include "../../cudacam_b200/csrc/k_stencil_march.cuh"
 #endif
 
 static void fill_gk(float gk[25])
@@ -23,7 +24,7 @@ static void fill_gk(float gk[25])
 }
 
 extern "C" {
-// impl: 1 = tile kernel (EMIT when any stage pointer is given), 0 = fused kernel
+// impl: 1 = tile kernel (EMIT when any stage pointer is given), 0 = fused CTA-tile kernel, 100 + rb = marching kernel with rb rows per band
 __attribute__((visibility("default"))) int emu_stencil(int impl, const uint8_t *bgr, long long row_stride, long long frame_stride, int w, int h, int y0, int h_glob, int nframes,
                                                        unsigned lo, unsigned hi, uint32_t *map2, uint8_t *mono, uint8_t *blur, float *grad, uint8_t *nms, uint8_t *thresh)
 {
@@ -54,6 +55,7 @@ __attribute__((visibility("default"))) int emu_stencil(int impl, const uint8_t *
     return 0;
   }
 #ifdef B2C_EMU_FUSED
+  if (impl >= 100) return b2c::march_emu_launch(p, impl - 100);   // impl = 100 + rows per band
   return b2c::fused_emu_launch(p);
 #else
   return -1;

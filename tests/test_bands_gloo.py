@@ -44,7 +44,7 @@ class EmuBandBackend:
         impl = 0 if self.width % 8 == 0 else 1
         a = self.buf.numpy()
         if impl == 0:
-            self._map2 = E.stencil_raw(a, bands.HALO, self.width, self.rows, impl=0, y0=self.y0, h_glob=self.height_global)
+            self._map2 = E.stencil_raw(a, bands.HALO, self.width, self.rows, impl=126, y0=self.y0, h_glob=self.height_global)
         else:
             f = np.ascontiguousarray(a[:, :self.width * 3]).reshape(a.shape[0], self.width, 3)
             self._map2 = E.stencil(f, impl=1, y0=self.y0, h_glob=self.height_global, rows=self.rows, row0=bands.HALO)["map2"][0]

@@ -26,15 +26,17 @@ FUSED_CASES = [("scene", 200, 150, 7, 10, 40), ("noise", 96, 61, 8, 10, 40), ("s
                ("steps", 480, 130, 2, 3, 200), ("scene", 8, 8, 1, 0, 0), ("noise", 488, 64, 3, 10, 40), ("scene", 720, 64, 3, 10, 40)]
 
 
+@pytest.mark.parametrize("impl", [0, 116, 136], ids=["fused", "march16", "march36"])
 @pytest.mark.parametrize("kind,w,h,seed,lo,hi", FUSED_CASES)
-def test_fused_stencil_map(kind, w, h, seed, lo, hi):
+def test_fused_stencil_map(kind, w, h, seed, lo, hi, impl):
+    """impl 0 = fused CTA-tile kernel, 100 + rb = marching warp-per-strip kernel with rb rows per band."""
     f = synth.frame(kind, seed, w, h)
     r = O.canny(f, lo, hi, want_edges=False)
-    # the fused kernel wants 16-byte aligned rows: give it a padded copy like the host driver does
+    # these kernels want 16-byte aligned rows: give them a padded copy like the host driver does
     stride = (w * 3 + 15) // 16 * 16
     buf = np.zeros((h + 8, stride), np.uint8)
     buf[4:4 + h, :w * 3] = f.reshape(h, w * 3)
-    e = E.stencil_raw(buf, 4, w, h, lo, hi, impl=0)
+    e = E.stencil_raw(buf, 4, w, h, lo, hi, impl=impl)
     if e is None:
         pytest.skip("fused kernel not in the emulator build")
     assert np.array_equal(e, O.thresh_to_map2(r["thresh"]))
@@ -86,26 +88,28 @@ def test_band_mode_stencil_equals_whole_image():
     assert np.array_equal(band, whole[y0:y0 + rows])
 
 
+@pytest.mark.parametrize("impl", [0, 126], ids=["fused", "march"])
 @pytest.mark.parametrize("v", [0, 3, 100, 255])
-def test_fused_flat_picture_takes_dense_replay(v):
+def test_fused_flat_picture_takes_dense_replay(v, impl):
     """Flat regions make S % 159 == 0 for every pixel: the work list overflows and the dense replay runs."""
     f = np.full((70, 248, 3), v, np.uint8)
     f[30:40, 100:140] = (v + 60) % 256
     r = O.canny(f, 10, 40, want_edges=False)
     buf = np.zeros((78, 752), np.uint8)
     buf[4:74, :744] = f.reshape(70, -1)
-    e = E.stencil_raw(buf, 4, 248, 70, 10, 40, impl=0)
+    e = E.stencil_raw(buf, 4, 248, 70, 10, 40, impl=impl)
     assert e is not None and np.array_equal(e, O.thresh_to_map2(r["thresh"]))
 
 
-def test_fused_band_mode_equals_whole_image():
+@pytest.mark.parametrize("impl", [0, 126], ids=["fused", "march"])
+def test_fused_band_mode_equals_whole_image(impl):
     w, h = 248, 150
     f = synth.frame("scene", 23, w, h)
     whole = O.thresh_to_map2(O.canny(f, want_edges=False)["thresh"])
     buf = np.zeros((h, 752), np.uint8)
     buf[:, :w * 3] = f.reshape(h, -1)
     for y0, rows in ((0, 50), (50, 61), (111, 39)):
-        band = E.stencil_raw(buf, y0, w, rows, impl=0, y0=y0, h_glob=h)
+        band = E.stencil_raw(buf, y0, w, rows, impl=impl, y0=y0, h_glob=h)
         assert np.array_equal(band, whole[y0:y0 + rows]), (y0, rows)
 
 
