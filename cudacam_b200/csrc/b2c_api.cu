@@ -44,6 +44,8 @@ struct b2c_ctx {
   uint8_t lo = 10, hi = 40;   // src/cvp/cannyEdgeH.cu:22-23
   bool profiling = true;      // src/cvp/cannyEdgeH.cu:24
   int stencil_impl = 0;       // 0 marching warp-per-strip kernel, 1 staged tile kernel, 2 fused CTA-tile kernel
+  int march_rb = 0;           // rows per band of the marching kernel, 0 = automatic
+  int march_stagger_ns = 4000;
   int hyst_impl = 0;          // 0 union-find (constant number of phases), 1 tile rounds
   int hyst_tile_rows = 16;
   int hyst_max_rounds = 1 << 20;
@@ -219,6 +221,7 @@ void fill_stencil_params(b2c_ctx *c, B2cStencilParams &p, const uint8_t *bgr, si
   p.n_wrap[1] = ldexpf(1048576.0f, -48);   // 4*512^2
   p.pitch8 = c->pitch8;
   p.pitchf = c->pitchf;
+  p.stagger_ns = c->march_stagger_ns;
 }
 
 // Fused stencil: BGR8 -> 2-bit map for n frames.
@@ -227,7 +230,7 @@ int launch_stencil(b2c_ctx *c, const uint8_t *bgr, size_t row_stride, size_t fra
   B2cStencilParams p;
   fill_stencil_params(c, p, bgr, row_stride, frame_stride, n);
   if (c->stencil_impl == 0 && b2c::march_supported(p)) {
-    cudaError_t e = b2c::march_launch(p, c->sm_count, st);
+    cudaError_t e = b2c::march_launch(p, c->sm_count, c->march_rb, st);
     if (e != cudaSuccess) return set_err(c, e, "k_stencil_march launch");
   } else if (c->stencil_impl == 2 && b2c::fused_supported(p)) {
     cudaError_t e = b2c::fused_launch(p, c->sm_count, st);
@@ -870,6 +873,16 @@ int b2c_set_option(b2c_handle c, const char *name, int value)
   if (!strcmp(name, "stencil_impl")) {
     if (value < 0 || value > 2) return B2C_ERR_INVALID;
     c->stencil_impl = value;
+    return B2C_OK;
+  }
+  if (!strcmp(name, "march_stagger_ns")) {
+    if (value < 0) return B2C_ERR_INVALID;
+    c->march_stagger_ns = value;
+    return B2C_OK;
+  }
+  if (!strcmp(name, "march_rb")) {
+    if (value < 0) return B2C_ERR_INVALID;
+    c->march_rb = value;
     return B2C_OK;
   }
   if (!strcmp(name, "hyst_impl")) {

@@ -55,6 +55,7 @@ struct B2cStencilParams {
   uint8_t *mono, *blur, *nms, *thresh;
   float *grad;
   int pitch8, pitchf;        // in elements
+  int stagger_ns;            // marching kernel: maximum start delay of a warp (phase spreading), 0 = none
 };
 
 struct B2cHystParams {

@@ -154,6 +154,15 @@ __global__ void __launch_bounds__(32, MARCH_CTAS_PER_SM) k_stencil_march(const B
       make_uint2(__byte_perm(m[0], m[1], 0x6420), __byte_perm(m[2], m[3], 0x6420));
   };
 
+#if !defined(B2C_EMU)
+  // De-synchronise the warps of an SM: stage A is alu-pipe work, stage C fma-pipe work; warps that start together
+  // stay in the same stage and fight for one pipe while the other idles.  A pseudo-random start delay of up to one
+  // block period spreads the phases (measured: 1.4x on the 64 x 1080p batch).
+  if (p.stagger_ns > 0) {
+    const unsigned bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    __nanosleep(((bid * 2654435761u) >> 24) * (unsigned)p.stagger_ns >> 8);
+  }
+#endif
   // ---- prologue: gray rows -4 .. -1 into window slots 1 .. 4 -----------------------------------------------
   uint32_t win[5][4];
   uint2 pre[3];   // raw BGR of the next gray row, in flight while the current row is processed
@@ -401,30 +410,29 @@ inline bool march_supported(const B2cStencilParams &p)
 {
   return p.w % 8 == 0 && p.w >= 8 && p.row_stride % 8 == 0 && p.frame_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(p.bgr) & 7) == 0;
 }
-// rows per band: bands of 10k-4 rows waste no block; pick the count that minimises (waves of resident warps) x (rows
-// a warp marches, incl. the 8 halo rows and the pipeline tail)
+// Rows per band.  Bands of 10k-4 rows waste no block (a band of rb rows runs ceil((rb+4)/10) blocks of 10 rows).
+// Measured on B200 (tools/sweep_rb.py): the kernel wants every SM full of warps all the time, so MANY short CTAs
+// (the block scheduler balances them; 36 rows = 11 % recompute) beat one wave of long ones (276 rows = 4 %
+// recompute but a ragged tail): 289 us vs 336 us on 64 x 1080p.  Cost model: waves x rows marched per CTA, with a
+// penalty for few waves.
 inline int march_band_rows(int w, int h, int nframes, int sm_count)
 {
-  const long long slots = (long long)sm_count * MARCH_CTAS_PER_SM;
+  const double slots = (double)sm_count * MARCH_CTAS_PER_SM;
   const long long strips = (w + MT_X - 1) / MT_X;
-  int best_rb = h;
+  int best_rb = MK - 4;
   double best = 1e30;
-  for (int k = 2; k <= (h + 4 + MK - 1) / MK + 1; ++k) {
+  for (int k = 1; k <= (h + 4 + MK - 1) / MK; ++k) {
     const int rb = MK * k - 4;
     const long long nb = (h + rb - 1) / rb;
-    const long long ctas = strips * nb * nframes;
-    const long long waves = (ctas + slots - 1) / slots;
-    // a partially filled machine runs each warp faster, but not proportionally: saturate at ~4 warps per SM
-    const double fill = (double)ctas / (double)(waves * slots);
-    const double speed = fill < 0.3 ? 0.3 / (fill > 0.02 ? fill : 0.02) : 1.0;   // per-warp speed-up when the SMs are not full
-    const double cost = (double)waves * (rb + 14) / (speed < 3.5 ? speed : 3.5);
+    const double waves = (double)(strips * nb * nframes) / slots;
+    const double cost = ceil(waves) * (MK * k + 3) * (1.0 + 0.5 / (waves > 1.0 ? waves : 1.0));
     if (cost < best) { best = cost; best_rb = rb; }
   }
   return best_rb;
 }
-inline cudaError_t march_launch(const B2cStencilParams &p, int sm_count, cudaStream_t st)
+inline cudaError_t march_launch(const B2cStencilParams &p, int sm_count, int rb_override, cudaStream_t st)
 {
-  const int rb = march_band_rows(p.w, p.h, p.nframes, sm_count);
+  const int rb = rb_override > 0 ? rb_override : march_band_rows(p.w, p.h, p.nframes, sm_count);
   dim3 grid((p.w + MT_X - 1) / MT_X, (p.h + rb - 1) / rb, p.nframes);
   k_stencil_march<<<grid, 32, MARCH_SMEM, st>>>(p, rb);
   return cudaGetLastError();
