@@ -46,7 +46,7 @@ struct b2c_ctx {
   int stencil_impl = 0;       // 0 marching warp-per-strip kernel, 1 staged tile kernel, 2 fused CTA-tile kernel
   int march_rb = 0;           // rows per band of the marching kernel, 0 = automatic
   int march_stagger_ns = 4000;
-  int hyst_impl = 0;          // 0 union-find (constant number of phases), 1 tile rounds
+  int hyst_impl = 0;          // 0 union-find as 4 launches, 1 tile rounds (cooperative), 2 union-find as one cooperative launch
   int hyst_tile_rows = 16;
   int hyst_max_rounds = 1 << 20;
 
@@ -188,6 +188,8 @@ int alloc_common(b2c_ctx *c)
     return B2C_ERR_CUDA;
   }
   c->uf_grid = c->sm_count * per_sm;
+  CK(c, cudaFuncSetAttribute(b2c::k_uf_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2c::UT_SMEM));
+  CK(c, cudaFuncSetAttribute(b2c::k_uf_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2c::UT_SMEM));
   CK(c, cudaFuncSetAttribute(b2c::k_stencil_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2c::TILE_SMEM));
   CK(c, cudaFuncSetAttribute(b2c::k_stencil_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2c::TILE_SMEM));
   if (b2c::march_configure() != cudaSuccess) return set_err(c, cudaGetLastError(), "march_configure");
@@ -297,6 +299,18 @@ int launch_hysteresis(b2c_ctx *c, int n, uint8_t *edges, size_t edges_pitch, siz
   p.parent_frame_stride = (long long)c->rows_alloc * c->plane_pitch * 32;
   void *args[] = { &p };
   if (c->hyst_impl == 0) {
+    // union-find as four ordinary launches (build, union, resolve, expand) -- no barrier inside, no host round trip between
+    const long long nwords = (long long)n * c->rows_alloc * c->wpr;
+    const unsigned gl = (unsigned)std::max<long long>(1, std::min<long long>((nwords + b2c::UFK_THREADS - 1) / b2c::UFK_THREADS, (long long)c->sm_count * 64));
+    const dim3 gt((c->wpr + b2c::UT_WORDS - 1) / b2c::UT_WORDS, (c->rows_alloc + b2c::UT_ROWS - 1) / b2c::UT_ROWS, n);
+    if (skip_init) b2c::k_uf_tile<true><<<gt, b2c::UT_THREADS, b2c::UT_SMEM, st>>>(p);
+    else b2c::k_uf_tile<false><<<gt, b2c::UT_THREADS, b2c::UT_SMEM, st>>>(p);
+    b2c::k_uf_border<<<gl, b2c::UFK_THREADS, 0, st>>>(p);
+    if (edges && !skip_expand) b2c::k_uf_resolve<true><<<gl, b2c::UFK_THREADS, 0, st>>>(p);
+    else b2c::k_uf_resolve<false><<<gl, b2c::UFK_THREADS, 0, st>>>(p);
+    c->launches += 2;
+    CK(c, cudaGetLastError());
+  } else if (c->hyst_impl != 1) {
     // one warp per plane row, at most one full wave of CTAs
     const long long rows = (long long)n * c->rows_alloc;
     const int wpb = b2c::UF_THREADS / 32;
@@ -886,7 +900,7 @@ int b2c_set_option(b2c_handle c, const char *name, int value)
     return B2C_OK;
   }
   if (!strcmp(name, "hyst_impl")) {
-    if (value < 0 || value > 1) return B2C_ERR_INVALID;
+    if (value < 0 || value > 2) return B2C_ERR_INVALID;
     c->hyst_impl = value;
     return B2C_OK;
   }

@@ -67,6 +67,13 @@ __device__ __forceinline__ void uf_union(int *P, int a, int b)
   }
 }
 
+// lowest bit of the run of ones of X that contains bit k (X has bit k set)
+__device__ __forceinline__ int uf_run_head(uint32_t X, int k)
+{
+  const uint32_t inv = ~X & ((1u << k) - 1u);   // zeros below k
+  return inv ? 32 - __clz((int)inv) : 0;
+}
+
 // ---- per-word bodies of the three sparse phases -------------------------------------------------------------------
 // B: parents of the weak pixels of one word
 __device__ __forceinline__ void uf_init_word(const B2cHystParams &p, int f, int y, int xw, uint32_t wd, uint32_t sM, int W32)
@@ -94,19 +101,21 @@ __device__ __forceinline__ void uf_init_word(const B2cHystParams &p, int f, int 
   }
 }
 
-// C: one union per (run, touching fragment of the row above / previous word): a run already shares one parent
-__device__ __forceinline__ void uf_union_word(const B2cHystParams &p, int f, int y, int xw, int W32)
+// C: one union per (run, touching fragment of the row above / previous word): a run already shares one parent.
+// doW / doN / doNW / doNE select which adjacencies are united here (the tile kernel has already united the ones that
+// stay inside a tile).
+__device__ __forceinline__ void uf_union_word(const B2cHystParams &p, int f, int y, int xw, int W32, bool doW = true, bool doN = true, bool doNW = true, bool doNE = true)
 {
   const int pp = p.plane_pitch;
   const long long o = f * p.plane_frame_stride + (long long)y * pp + xw;
   const uint32_t wd = p.C[o] & ~p.S[o];
   if (wd == 0u) return;
-  const uint32_t wl = xw > 0 ? (p.C[o - 1] & ~p.S[o - 1]) : 0u;
+  const uint32_t wl = (doW && xw > 0) ? (p.C[o - 1] & ~p.S[o - 1]) : 0u;
   uint32_t wu = 0u, wul = 0u, wur = 0u;
   if (y > 0) {
-    wu = p.C[o - pp] & ~p.S[o - pp];
-    if (xw > 0) wul = p.C[o - pp - 1] & ~p.S[o - pp - 1];
-    if (xw + 1 < pp) wur = p.C[o - pp + 1] & ~p.S[o - pp + 1];
+    if (doN) wu = p.C[o - pp] & ~p.S[o - pp];
+    if (doNW && xw > 0) wul = p.C[o - pp - 1] & ~p.S[o - pp - 1];
+    if (doNE && xw + 1 < pp) wur = p.C[o - pp + 1] & ~p.S[o - pp + 1];
   }
   int *P = p.parent + f * p.parent_frame_stride;
   const int base = y * W32 + xw * 32 + 1;
@@ -116,15 +125,16 @@ __device__ __forceinline__ void uf_union_word(const B2cHystParams &p, int f, int
     const uint32_t run = m & ~(m + lo);
     m &= ~run;
     const int n = base + __ffs((int)lo) - 1;
-    if ((run & 1u) && (wl >> 31)) uf_union(P, n, n - 1);                 // W neighbour in the previous word
-    uint32_t a = (run | (run << 1) | (run >> 1)) & wu;                   // N / NW / NE inside this word column
+    // every union partner is named by the HEAD of its run inside its word (the only pixels the tile kernel gives a parent)
+    if ((run & 1u) && (wl >> 31)) uf_union(P, n, base - 32 + uf_run_head(wl, 31));      // W neighbour in the previous word
+    uint32_t a = (run | (run << 1) | (run >> 1)) & wu;                                 // N / NW / NE inside this word column
     while (a) {
       const uint32_t lo2 = a & (0u - a);
-      a &= (a + lo2);                                                    // drop the fragment that starts at lo2
-      uf_union(P, n, base - W32 + __ffs((int)lo2) - 1);
+      a &= (a + lo2);                                                                  // drop the fragment that starts at lo2
+      uf_union(P, n, base - W32 + uf_run_head(wu, __ffs((int)lo2) - 1));
     }
-    if ((run & 1u) && (wul >> 31)) uf_union(P, n, base - W32 - 1);       // NW across the word boundary
-    if ((run >> 31) && (wur & 1u)) uf_union(P, n, base - W32 + 32);      // NE across the word boundary
+    if ((run & 1u) && (wul >> 31)) uf_union(P, n, base - W32 - 32 + uf_run_head(wul, 31));   // NW across the word boundary
+    if ((run >> 31) && (wur & 1u)) uf_union(P, n, base - W32 + 32);                         // NE across the word boundary (bit 0 is a head)
   }
 }
 
@@ -275,5 +285,275 @@ __global__ void __launch_bounds__(UF_THREADS) k_hysteresis_uf(const B2cHystParam
   }
   B2C_STAMP(5);
 #undef B2C_FOR_WORDS
+}
+
+// =====================================================================================================================
+// The same union-find as FOUR ordinary launches on one stream (no host round trip between them):
+//   k_uf_tile (planes + tile-local union-find in shared memory) -> k_uf_border -> k_uf_resolve -> k_uf_expand.
+// Kernel boundaries replace the grid-wide barriers and fences of the cooperative version, every phase gets its own
+// thread mapping (one thread per plane word; words without weak pixels leave at once) and the block scheduler
+// balances the load.  No work list and no counter: a same-address atomic per warp (list append, "changed" flag) cost
+// more than the phases themselves (measured 50-95 us per 32 frames).
+// =====================================================================================================================
+constexpr int UFK_THREADS = 256;
+
+// ---- tile build: the union-find of a 32-row x 256-pixel tile entirely in shared memory ------------------------------
+// Concurrent unions on a long weak line build a parent chain as long as the line (every run hooks under the run above
+// it at the same time), and every later find() walks it with two dependent L2 round trips per step: measured 85 +
+// 85 us for the union and resolve phases of 32 x 1080p however well the load was balanced.  So the chains are built
+// and FLATTENED where a step costs ~30 cycles: one CTA per tile, one thread per plane word, parents in shared memory,
+// local unions (W / N / NW / NE inside the tile), then every weak pixel's GLOBAL parent is written as the root of its
+// tile-local tree (or 0 = "touches a strong pixel").  What remains for global memory are the unions across tile
+// borders (k_uf_border) on trees whose depth is the number of tile crossings, not the number of pixels.
+constexpr int UT_ROWS = 32, UT_WORDS = 8, UT_THREADS = UT_ROWS * UT_WORDS;
+constexpr int UT_OFF_LW = (UT_ROWS * UT_WORDS * 32 + 4) * 4, UT_OFF_LS = UT_OFF_LW + UT_THREADS * 4, UT_OFF_IT = UT_OFF_LS + UT_THREADS * 4,
+              UT_OFF_WC = UT_OFF_IT + UT_THREADS * 2, UT_SMEM = UT_OFF_WC + 64;
+
+__device__ __forceinline__ int ut_find(int *P, int n)
+{
+  while (n != 0) {
+    const int pn = P[n];
+    if (pn == n || pn == 0) return pn;
+    const int gp = P[pn];
+    if (gp == pn) return pn;
+    atomicMin(P + n, gp);
+    n = gp;
+  }
+  return n;
+}
+__device__ __forceinline__ void ut_union(int *P, int a, int b)
+{
+  for (;;) {
+    a = ut_find(P, a);
+    b = ut_find(P, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }
+    const int old = atomicMin(P + a, b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+template <bool REENTRY>
+__global__ void __launch_bounds__(UT_THREADS) k_uf_tile(const B2cHystParams p)
+{
+  B2C_DYN_SMEM(smem);
+  int *LP = reinterpret_cast<int *>(smem);                                   // local parents (run heads only), node 0 = strong
+  uint32_t *LW = reinterpret_cast<uint32_t *>(smem + UT_OFF_LW);             // weak words of the tile
+  uint32_t *LS = reinterpret_cast<uint32_t *>(smem + UT_OFF_LS);             // strong words of the tile
+  uint16_t *IT = reinterpret_cast<uint16_t *>(smem + UT_OFF_IT);             // compacted list: tile positions of the words with weak pixels
+  int *WC = reinterpret_cast<int *>(smem + UT_OFF_WC);                       // per-warp counts
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wpr = (p.w + 31) >> 5;
+  const int f = blockIdx.z, y0 = blockIdx.y * UT_ROWS, xw0 = blockIdx.x * UT_WORDS;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) { p.flags[3] = 1; p.flags[4] = 0; }
+  {   // ---- phase 0, one thread per plane word: S / C planes, tile copies, compaction of the words with weak pixels
+    const int ly = tid >> 3, lw = tid & 7, y = y0 + ly, xw = xw0 + lw;
+    uint32_t wd = 0u, sM = 0u;
+    if (y < p.h && xw < wpr) {
+      const long long o = f * p.plane_frame_stride + (long long)y * p.plane_pitch + xw;
+      if (REENTRY) {
+        sM = p.S[o];
+        wd = p.C[o] & ~sM;
+      } else {
+        const uint32_t *mrow = p.map2 + f * p.map_frame_stride + (long long)y * p.map_pitch;
+        const uint32_t m0 = mrow[2 * xw], m1 = (2 * xw + 1 < p.map_pitch) ? mrow[2 * xw + 1] : 0u;
+        sM = (m0 & 0xFFFFu) | (m1 << 16);
+        wd = (m0 >> 16) | (m1 & 0xFFFF0000u);
+        p.S[o] = sM;
+        p.C[o] = sM | wd;
+      }
+    }
+    LW[tid] = wd;
+    LS[tid] = sM;
+    const uint32_t mask = __ballot_sync(B2C_FULL, wd != 0u);
+    if (lane == 0) WC[warp] = __popc(mask);
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < UT_THREADS / 32; ++w) {
+      const int c = WC[w];
+      if (w < warp) before += c;
+      total += c;
+    }
+    if (wd) IT[before + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)tid;
+    if (tid == 0) WC[UT_THREADS / 32] = total;
+  }
+  __syncthreads();
+  const int nitems = WC[UT_THREADS / 32];
+  // ---- the remaining phases run on the compacted list: thread k takes the k-th word that holds weak pixels, so the
+  // divergent per-run loops fill whole warps instead of a few lanes of every warp
+  const bool act = tid < nitems;
+  const int t = act ? IT[tid] : 0, ly = t >> 3, lw = t & 7, y = y0 + ly, xw = xw0 + lw;
+  const uint32_t wd = act ? LW[t] : 0u;
+  const int lbase = 1 + t * 32;   // local node of bit 0 of this word
+  if (act) {
+    // strong bits of the 3x3 neighbourhood, on words: from the tile copy, or from global memory outside the tile.
+    // Rows -1 and h are the ghost rows of the S plane; inside the frame the words are rebuilt from the map (the S
+    // words of other tiles may not have been written yet).
+    const int pp = p.plane_pitch;
+    const uint32_t *Sr = p.S + f * p.plane_frame_stride + (long long)y * pp + xw;
+    auto srow = [&](int dy, int dx) -> uint32_t {   // S word (y + dy, xw + dx)
+      const int l2 = ly + dy, w2 = lw + dx, x2 = xw + dx, yy = y + dy;
+      if (x2 < 0 || x2 >= wpr) return 0u;
+      if (l2 >= 0 && l2 < UT_ROWS && yy < p.h && w2 >= 0 && w2 < UT_WORDS) return LS[l2 * UT_WORDS + w2];   // (row h is a ghost row: global)
+      if (REENTRY || yy < 0 || yy >= p.h) return __ldcg(Sr + (long long)dy * pp + dx);
+      const uint32_t *mr = p.map2 + f * p.map_frame_stride + (long long)yy * p.map_pitch;
+      const uint32_t a = mr[2 * x2], b = (2 * x2 + 1 < p.map_pitch) ? mr[2 * x2 + 1] : 0u;
+      return (a & 0xFFFFu) | (b << 16);
+    };
+    uint32_t v = LS[t] | srow(-1, 0) | srow(1, 0), vl = 0u, vr = 0u;
+    if (wd & 1u) vl = srow(-1, -1) | srow(0, -1) | srow(1, -1);
+    if (wd >> 31) vr = srow(-1, 1) | srow(0, 1) | srow(1, 1);
+    const uint32_t near = wd & (v | (v << 1) | (v >> 1) | (vl >> 31) | (vr << 31));
+    uint32_t m = wd;
+    while (m) {
+      const uint32_t lo = m & (0u - m);
+      const uint32_t run = m & ~(m + lo);   // the run of ones that starts at the lowest set bit
+      m &= ~run;
+      const int n = lbase + __ffs((int)lo) - 1;
+      LP[n] = (run & near) ? 0 : n;
+    }
+  }
+  __syncthreads();
+  if (act) {   // local unions: W, and N / NW / NE with the row above, inside the tile
+    const uint32_t wl = lw > 0 ? LW[t - 1] : 0u;
+    uint32_t wu = 0u, wul = 0u, wur = 0u;
+    if (ly > 0) {
+      wu = LW[t - UT_WORDS];
+      if (lw > 0) wul = LW[t - UT_WORDS - 1];
+      if (lw + 1 < UT_WORDS) wur = LW[t - UT_WORDS + 1];
+    }
+    uint32_t m = wd;
+    while (m) {
+      const uint32_t lo = m & (0u - m);
+      const uint32_t run = m & ~(m + lo);
+      m &= ~run;
+      const int n = lbase + __ffs((int)lo) - 1;
+      if ((run & 1u) && (wl >> 31)) ut_union(LP, n, lbase - 32 + uf_run_head(wl, 31));
+      uint32_t a = (run | (run << 1) | (run >> 1)) & wu;
+      while (a) {
+        const uint32_t lo2 = a & (0u - a);
+        a &= (a + lo2);
+        ut_union(LP, n, lbase - UT_WORDS * 32 + uf_run_head(wu, __ffs((int)lo2) - 1));
+      }
+      if ((run & 1u) && (wul >> 31)) ut_union(LP, n, lbase - UT_WORDS * 32 - 32 + uf_run_head(wul, 31));
+      if ((run >> 31) && (wur & 1u)) ut_union(LP, n, lbase - UT_WORDS * 32 + 32);
+    }
+  }
+  __syncthreads();
+  if (act) {   // global parents of the run heads = tile-local roots
+    const int W32 = p.plane_pitch * 32;
+    int *P = p.parent + f * p.parent_frame_stride;
+    const int gbase = y * W32 + xw * 32;   // global node of bit b = gbase + b + 1, stored at P[gbase + b]
+    uint32_t m = wd;
+    while (m) {
+      const uint32_t lo = m & (0u - m);
+      const uint32_t run = m & ~(m + lo);
+      m &= ~run;
+      const int hb = __ffs((int)lo) - 1;
+      int r = lbase + hb;
+      for (;;) {   // plain walk: the local trees are final now
+        const int pr = LP[r];
+        if (pr == r || pr == 0) { r = pr; break; }
+        r = pr;
+      }
+      int val = 0;
+      if (r != 0) {
+        const int q = r - 1;   // local pixel index: (row * 8 + word) * 32 + bit
+        val = (y0 + (q >> 8)) * W32 + xw0 * 32 + (q & 255) + 1;
+      }
+      P[gbase + hb] = val;
+    }
+  }
+}
+
+// unions across tile borders (everything k_uf_tile could not see); one thread per plane word
+__global__ void __launch_bounds__(UFK_THREADS) k_uf_border(const B2cHystParams p)
+{
+  const int wpr = (p.w + 31) >> 5, W32 = p.plane_pitch * 32;
+  const long long nwords = (long long)p.nframes * p.h * wpr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (long long)gridDim.x * blockDim.x) {
+    const int row_ = (int)(i / wpr), xw = (int)(i - (long long)row_ * wpr), f = row_ / p.h, y = row_ - f * p.h;
+    const bool top = (y % UT_ROWS) == 0, left = (xw % UT_WORDS) == 0, right = (xw % UT_WORDS) == UT_WORDS - 1;
+    if (top || left || right) uf_union_word(p, f, y, xw, W32, left, top, top || left, top || right);
+  }
+}
+
+// a run survives iff its root is node 0; then (EXPAND) the final S word goes out as 32 bytes of the u8 {0,255} edge map.
+// One thread per plane word.
+template <bool EXPAND>
+__global__ void __launch_bounds__(UFK_THREADS) k_uf_resolve(const B2cHystParams p)
+{
+  const int wpr = (p.w + 31) >> 5, W32 = p.plane_pitch * 32;
+  const long long nwords = (long long)p.nframes * p.h * wpr;
+  bool changed = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (long long)gridDim.x * blockDim.x) {
+    const int row_ = (int)(i / wpr), xw = (int)(i - (long long)row_ * wpr), f = row_ / p.h, y = row_ - f * p.h;
+    const long long o = f * p.plane_frame_stride + (long long)y * p.plane_pitch + xw;
+    uint32_t s = p.S[o];
+    uint32_t m = p.C[o] & ~s;
+    if (m) {
+      int *P = p.parent + f * p.parent_frame_stride;
+      const int base = y * W32 + xw * 32 + 1;
+      uint32_t add = 0u;
+      while (m) {
+        const uint32_t lo = m & (0u - m);
+        const uint32_t run = m & ~(m + lo);
+        m &= ~run;
+        if (uf_find_final(P, base + __ffs((int)lo) - 1) == 0) add |= run;
+      }
+      if (add) {
+        s |= add;
+        p.S[o] = s;
+        changed = true;
+      }
+    }
+    if (EXPAND) {
+      uint8_t *out = p.edges + f * p.edges_frame_stride + (long long)y * p.edges_pitch + xw * 32;
+      const int n = min(32, p.w - xw * 32);
+      if (n == 32 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const uint32_t bits = (s >> (16 * hh)) & 0xFFFFu;
+          uint4 v;
+          v.x = (((bits & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+          v.y = ((((bits >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+          v.z = ((((bits >> 8) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+          v.w = ((((bits >> 12) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+          reinterpret_cast<uint4 *>(out)[hh] = v;
+        }
+      } else {
+        for (int k = 0; k < n; ++k) out[k] = ((s >> k) & 1u) ? 255 : 0;
+      }
+    }
+  }
+  // one plain store per warp at most, and only while the flag is still clear (a same-address atomic per thread
+  // serialises in L2 and cost more than the whole phase)
+  if (__any_sync(B2C_FULL, changed) && (threadIdx.x & 31) == 0 && __ldcg(p.flags + 4) == 0) __stcg(p.flags + 4, 1);
+}
+
+// expand: S plane -> u8 {0,255}; one thread per 16 pixels (one 128-bit store)
+__global__ void __launch_bounds__(UFK_THREADS) k_uf_expand(const B2cHystParams p)
+{
+  const int gpr = (p.w + 15) >> 4;
+  const long long total = (long long)p.nframes * p.h * gpr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int row_ = (int)(i / gpr), g = (int)(i - (long long)row_ * gpr), f = row_ / p.h, y = row_ - f * p.h;
+    const uint32_t word = p.S[f * p.plane_frame_stride + (long long)y * p.plane_pitch + (g >> 1)];
+    const uint32_t bits = (word >> ((g & 1) * 16)) & 0xFFFFu;
+    uint8_t *out = p.edges + f * p.edges_frame_stride + (long long)y * p.edges_pitch + g * 16;
+    const int n = min(16, p.w - g * 16);
+    if (n == 16 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+      uint4 v;
+      v.x = (((bits & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+      v.y = ((((bits >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+      v.z = ((((bits >> 8) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+      v.w = ((((bits >> 12) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+      *reinterpret_cast<uint4 *>(out) = v;
+    } else {
+      for (int k = 0; k < n; ++k) out[k] = ((bits >> k) & 1u) ? 255 : 0;
+    }
+  }
 }
 }// namespace b2c

@@ -84,8 +84,19 @@ __attribute__((visibility("default"))) int emu_hysteresis(const uint32_t *map2, 
   p.parent = parent.data(); p.parent_frame_stride = (long long)h * pitch * 32;
   if (tile_rows > 0)
     emu::launch(dim3(grid_blocks), dim3(b2c::HYST_THREADS), b2c::hyst_smem_bytes(tile_rows), true, [p] { b2c::k_hysteresis(p); });
-  else   // tile_rows == 0 selects the union-find kernel
+  else if (tile_rows == 0)   // the cooperative union-find kernel
     emu::launch(dim3(grid_blocks), dim3(b2c::UF_THREADS), b2c::UF_SMEM, true, [p] { b2c::k_hysteresis_uf(p); });
+  else {   // tile_rows < 0: union-find as four launches; ghost rows given => re-entry on planes built by a first pass
+    const int reps = (ghost_top || ghost_bot) ? 2 : 1;   // second repetition exercises the REENTRY build on the retained planes
+    const dim3 gt((wpr + b2c::UT_WORDS - 1) / b2c::UT_WORDS, (h + b2c::UT_ROWS - 1) / b2c::UT_ROWS, nframes);
+    for (int rep = 0; rep < reps; ++rep) {
+      if (rep == 0) emu::launch(gt, dim3(b2c::UT_THREADS), b2c::UT_SMEM, false, [p] { b2c::k_uf_tile<false>(p); });
+      else emu::launch(gt, dim3(b2c::UT_THREADS), b2c::UT_SMEM, false, [p] { b2c::k_uf_tile<true>(p); });
+      emu::launch(dim3(grid_blocks), dim3(b2c::UFK_THREADS), 0, false, [p] { b2c::k_uf_border(p); });
+      if (rep + 1 < reps) emu::launch(dim3(grid_blocks), dim3(b2c::UFK_THREADS), 0, false, [p] { b2c::k_uf_resolve<false>(p); });
+      else emu::launch(dim3(grid_blocks), dim3(b2c::UFK_THREADS), 0, false, [p] { b2c::k_uf_resolve<true>(p); });
+    }
+  }
   if (bits_out)
     for (int f = 0; f < nframes; ++f)
       for (int y = 0; y < h; ++y) memcpy(bits_out + ((size_t)f * h + y) * wpr, p.S + f * fs + (long long)y * pitch, wpr * 4);

@@ -54,7 +54,7 @@ class EmuBandBackend:
         # seeds that reaches the same fixpoint as the product's re-entry on the retained planes
         gt = self._g[0].numpy().view(np.uint32)
         gb = self._g[1].numpy().view(np.uint32)
-        edges, bits, _, _ = E.hysteresis(self._map2, self.width, grid_blocks=2, tile_rows=0, ghost_top=gt, ghost_bot=gb)
+        edges, bits, _, _ = E.hysteresis(self._map2, self.width, grid_blocks=2, tile_rows=-1, ghost_top=gt, ghost_bot=gb)
         self._edges = edges[0]
         self._b[0].copy_(torch.from_numpy(bits[0][0].view(np.int32).copy()))
         self._b[1].copy_(torch.from_numpy(bits[0][-1].view(np.int32).copy()))

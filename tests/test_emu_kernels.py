@@ -42,7 +42,7 @@ def test_fused_stencil_map(kind, w, h, seed, lo, hi, impl):
     assert np.array_equal(e, O.thresh_to_map2(r["thresh"]))
 
 
-@pytest.mark.parametrize("tile_rows", [0, 4], ids=["unionfind", "tilerounds"])
+@pytest.mark.parametrize("tile_rows", [-1, 0, 4], ids=["unionfind4", "unionfind_coop", "tilerounds"])
 @pytest.mark.parametrize("kind,w,h,seed", [("scene", 200, 150, 7), ("noise", 97, 61, 8), ("steps", 130, 70, 9), ("scene", 1100, 40, 5)])
 def test_hysteresis_kernel(kind, w, h, seed, tile_rows):
     f = synth.frame(kind, seed, w, h)
@@ -52,16 +52,17 @@ def test_hysteresis_kernel(kind, w, h, seed, tile_rows):
     assert np.array_equal(bits[0], O.edges_to_bits(r["edges"]))
 
 
+@pytest.mark.parametrize("tile_rows", [-1, 0], ids=["unionfind4", "unionfind_coop"])
 @pytest.mark.parametrize("dens", [0.1, 0.3, 0.5])
-def test_hysteresis_unionfind_random_maps(dens):
+def test_hysteresis_unionfind_random_maps(dens, tile_rows):
     rng = np.random.default_rng(int(dens * 10))
     t = np.where(rng.random((90, 131)) < dens, 128, 0).astype(np.uint8)
     t[rng.random(t.shape) < 0.002] = 255
-    edges, _, _, _ = E.hysteresis(O.thresh_to_map2(t), 131, grid_blocks=4, tile_rows=0)
+    edges, _, _, _ = E.hysteresis(O.thresh_to_map2(t), 131, grid_blocks=4, tile_rows=tile_rows)
     assert np.array_equal(edges[0], O.hysteresis(t))
 
 
-@pytest.mark.parametrize("tile_rows", [0, 4], ids=["unionfind", "tilerounds"])
+@pytest.mark.parametrize("tile_rows", [-1, 0, 4], ids=["unionfind4", "unionfind_coop", "tilerounds"])
 def test_hysteresis_long_chain_and_batch(tile_rows):
     # a weak spiral seeded by a single strong pixel: worst case for tile-local propagation
     w, h = 70, 40
@@ -120,3 +121,16 @@ def test_hysteresis_unionfind_word_list_overflow():
     t[rng.random(t.shape) < 0.001] = 255
     edges, _, _, _ = E.hysteresis(O.thresh_to_map2(t), 2048, grid_blocks=1, tile_rows=0)
     assert np.array_equal(edges[0], O.hysteresis(t))
+
+
+def test_hysteresis_unionfind4_ghost_rows_and_reentry():
+    """Row-band mode: strong bits in the ghost rows seed the band; the second pass re-enters on the retained planes."""
+    w, h = 100, 20
+    t = np.zeros((h, w), np.uint8)
+    t[0:h, 10] = 128          # reaches the top ghost row
+    t[5:h, 50] = 128          # reaches the bottom ghost row only
+    t[3:10, 80] = 128         # touches nothing
+    gt = np.zeros((w + 31) // 32, np.uint32); gt[0] = 1 << 11   # strong pixel at (-1, 11): diagonal neighbour of (0, 10)
+    gb = np.zeros((w + 31) // 32, np.uint32); gb[1] = 1 << (50 - 32)
+    edges, bits, _, changed = E.hysteresis(O.thresh_to_map2(t), w, grid_blocks=2, tile_rows=-1, ghost_top=gt, ghost_bot=gb)
+    assert edges[0][:, 10].all() and edges[0][5:, 50].all() and not edges[0][:, 80].any() and not edges[0][:5, 50].any()

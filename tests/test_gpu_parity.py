@@ -81,7 +81,7 @@ def test_live_reference_kernels_720p():
     ref.close()
 
 
-@pytest.mark.parametrize("hyst_impl", [0, 1], ids=["unionfind", "tilerounds"])
+@pytest.mark.parametrize("hyst_impl", [0, 1, 2], ids=["unionfind4", "tilerounds", "unionfind_coop"])
 def test_hysteresis_impls_and_worst_cases(hyst_impl):
     """Both on-device hysteresis schemes against the fixpoint oracle, incl. a 1910-px weak line seeded at one end
     (65 reference launches) and a dense random map."""
