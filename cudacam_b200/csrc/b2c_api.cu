@@ -68,6 +68,9 @@ struct b2c_ctx {
   float *d_grad = nullptr;
   int *d_flags = nullptr;
   int *d_parent = nullptr;
+  uint32_t *d_blist = nullptr;   // per-frame lists of tile-border words with weak pixels
+  int *d_bcount = nullptr;       // their lengths (zeroed again by the resolve kernel)
+  int bcap = 0;                  // entries per frame
   uint8_t *d_zeros = nullptr;
   int uf_grid = 0;
   int *h_flags = nullptr;   // pinned mirror
@@ -84,6 +87,8 @@ struct b2c_ctx {
   size_t h_in_bytes = 0, h_out_bytes = 0;
   cudaStream_t s_main = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_in[NSLOT] = {}, ev_k[NSLOT] = {}, ev_out[NSLOT] = {};
+  cudaEvent_t ev_h[4] = {};   // hysteresis phase marks (only with the hyst_phase_timing option)
+  bool hyst_phase_timing = false;
   cudaEvent_t ev_t[5] = {};   // timing marks: start, after upload, after stencil, after hysteresis, end
   bool timings_valid = false;
 
@@ -156,6 +161,13 @@ int alloc_common(b2c_ctx *c)
   CK(c, cudaMemset(c->d_C_base, 0, plane_bytes));
   CK(c, cudaMalloc(&c->d_edges, (size_t)nb * c->edges_frame_stride));
   CK(c, cudaMalloc(&c->d_parent, (size_t)nb * rows * c->plane_pitch * 32 * sizeof(int)));
+  {
+    const int ntr = (rows + b2c::UT_ROWS - 1) / b2c::UT_ROWS, ntc = (c->wpr + b2c::UT_WORDS - 1) / b2c::UT_WORDS;
+    c->bcap = ntr * c->wpr + 2 * ntc * rows;   // every word of the top rows + both border columns of every tile
+    CK(c, cudaMalloc(&c->d_blist, (size_t)nb * c->bcap * sizeof(uint32_t)));
+    CK(c, cudaMalloc(&c->d_bcount, (size_t)nb * sizeof(int)));
+    CK(c, cudaMemset(c->d_bcount, 0, (size_t)nb * sizeof(int)));
+  }
   CK(c, cudaMalloc(&c->d_zeros, 256));
   CK(c, cudaMemset(c->d_zeros, 0, 256));
   CK(c, cudaMalloc(&c->d_flags, 16 * sizeof(int)));
@@ -298,16 +310,25 @@ int launch_hysteresis(b2c_ctx *c, int n, uint8_t *edges, size_t edges_pitch, siz
   p.parent = c->d_parent;
   p.parent_frame_stride = (long long)c->rows_alloc * c->plane_pitch * 32;
   void *args[] = { &p };
-  if (c->hyst_impl == 0) {
+  if (c->hyst_impl == 0 && c->wpr <= 1024) {   // (list entries hold the word index in 10 bits: wider images take the cooperative kernel)
     // union-find as four ordinary launches (build, union, resolve, expand) -- no barrier inside, no host round trip between
-    const long long nwords = (long long)n * c->rows_alloc * c->wpr;
-    const unsigned gl = (unsigned)std::max<long long>(1, std::min<long long>((nwords + b2c::UFK_THREADS - 1) / b2c::UFK_THREADS, (long long)c->sm_count * 64));
     const dim3 gt((c->wpr + b2c::UT_WORDS - 1) / b2c::UT_WORDS, (c->rows_alloc + b2c::UT_ROWS - 1) / b2c::UT_ROWS, n);
-    if (skip_init) b2c::k_uf_tile<true><<<gt, b2c::UT_THREADS, b2c::UT_SMEM, st>>>(p);
-    else b2c::k_uf_tile<false><<<gt, b2c::UT_THREADS, b2c::UT_SMEM, st>>>(p);
-    b2c::k_uf_border<<<gl, b2c::UFK_THREADS, 0, st>>>(p);
-    if (edges && !skip_expand) b2c::k_uf_resolve<true><<<gl, b2c::UFK_THREADS, 0, st>>>(p);
-    else b2c::k_uf_resolve<false><<<gl, b2c::UFK_THREADS, 0, st>>>(p);
+    const bool pt = c->hyst_phase_timing;
+    if (pt) cudaEventRecord(c->ev_h[0], st);
+    if (skip_init) b2c::k_uf_tile<true><<<gt, b2c::UT_THREADS, b2c::UT_SMEM, st>>>(p, c->d_blist, c->d_bcount, c->bcap);
+    else b2c::k_uf_tile<false><<<gt, b2c::UT_THREADS, b2c::UT_SMEM, st>>>(p, c->d_blist, c->d_bcount, c->bcap);
+    if (pt) cudaEventRecord(c->ev_h[1], st);
+    {
+      // border list: typically ~12 % of bcap entries; a quarter of the worst case in blocks, grid-stride for the rest
+      const int T = b2c::UFK_THREADS, gb = std::max(1, (c->bcap / 4 + T - 1) / T);
+      b2c::k_uf_border<<<dim3(gb, 1, n), T, 0, st>>>(p, c->d_blist, c->d_bcount, c->bcap);
+      if (pt) cudaEventRecord(c->ev_h[2], st);
+      const int tx = c->wpr >= 256 ? 256 : c->wpr > 32 ? 64 : 32, ty = 256 / tx;   // 256 threads = tx words x ty rows
+      const dim3 gr((c->wpr + tx - 1) / tx, (c->rows_alloc + ty - 1) / ty, n), br(tx, ty);
+      if (edges && !skip_expand) b2c::k_uf_resolve<true><<<gr, br, 0, st>>>(p, c->d_bcount);
+      else b2c::k_uf_resolve<false><<<gr, br, 0, st>>>(p, c->d_bcount);
+      if (pt) cudaEventRecord(c->ev_h[3], st);
+    }
     c->launches += 2;
     CK(c, cudaGetLastError());
   } else if (c->hyst_impl != 1) {
@@ -424,6 +445,8 @@ void b2c_destroy(b2c_handle c)
   cudaFree(c->d_grad);
   cudaFree(c->d_flags);
   cudaFree(c->d_parent);
+  cudaFree(c->d_blist);
+  cudaFree(c->d_bcount);
   cudaFree(c->d_zeros);
   if (c->h_flags) cudaFreeHost(c->h_flags);
   for (int i = 0; i < NSLOT; ++i) {
@@ -434,6 +457,8 @@ void b2c_destroy(b2c_handle c)
     if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
   }
   for (auto &e : c->ev_t)
+    if (e) cudaEventDestroy(e);
+  for (auto &e : c->ev_h)
     if (e) cudaEventDestroy(e);
   if (c->s_main) cudaStreamDestroy(c->s_main);
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
@@ -894,6 +919,12 @@ int b2c_set_option(b2c_handle c, const char *name, int value)
     c->march_stagger_ns = value;
     return B2C_OK;
   }
+  if (!strcmp(name, "hyst_phase_timing")) {
+    c->hyst_phase_timing = value != 0;
+    if (c->hyst_phase_timing && !c->ev_h[0])
+      for (auto &e : c->ev_h) CK(c, cudaEventCreate(&e));
+    return B2C_OK;
+  }
   if (!strcmp(name, "march_rb")) {
     if (value < 0) return B2C_ERR_INVALID;
     c->march_rb = value;
@@ -920,6 +951,13 @@ int b2c_get_info(b2c_handle c, const char *name)
     if (cudaMemcpy(v, c->d_flags, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return B2C_ERR_CUDA;
     const int k = name[5] - '0';
     return (k >= 0 && k < 8) ? v[8 + k] : B2C_ERR_INVALID;
+  }
+  if (!strncmp(name, "hyst_phase_us", 13)) {   // phase times of the last union-find hysteresis run with "hyst_phase_timing" on (us)
+    const int k = name[13] - '0';
+    if (k < 0 || k > 2 || !c->ev_h[0]) return B2C_ERR_INVALID;
+    float ms = 0;
+    if (cudaEventSynchronize(c->ev_h[3]) != cudaSuccess || cudaEventElapsedTime(&ms, c->ev_h[k], c->ev_h[k + 1]) != cudaSuccess) return B2C_ERR_CUDA;
+    return (int)(ms * 1000.0f + 0.5f);
   }
   if (!strcmp(name, "hyst_grid")) return c->hyst_grid;
   if (!strcmp(name, "sm_count")) return c->sm_count;

@@ -74,6 +74,9 @@ __device__ __forceinline__ int uf_run_head(uint32_t X, int k)
   return inv ? 32 - __clz((int)inv) : 0;
 }
 
+// rank of the run that starts at bit hb among the runs of word X (a 32-bit word holds at most 16 runs)
+__device__ __forceinline__ int uf_run_rank(uint32_t X, int hb) { return __popc(X & ~(X << 1) & ((1u << hb) - 1u)); }
+
 // ---- per-word bodies of the three sparse phases -------------------------------------------------------------------
 // B: parents of the weak pixels of one word
 __device__ __forceinline__ void uf_init_word(const B2cHystParams &p, int f, int y, int xw, uint32_t wd, uint32_t sM, int W32)
@@ -306,7 +309,7 @@ constexpr int UFK_THREADS = 256;
 // tile-local tree (or 0 = "touches a strong pixel").  What remains for global memory are the unions across tile
 // borders (k_uf_border) on trees whose depth is the number of tile crossings, not the number of pixels.
 constexpr int UT_ROWS = 32, UT_WORDS = 8, UT_THREADS = UT_ROWS * UT_WORDS;
-constexpr int UT_OFF_LW = (UT_ROWS * UT_WORDS * 32 + 4) * 4, UT_OFF_LS = UT_OFF_LW + UT_THREADS * 4, UT_OFF_IT = UT_OFF_LS + UT_THREADS * 4,
+constexpr int UT_OFF_LW = (UT_ROWS * UT_WORDS * 16 + 4) * 4, UT_OFF_LS = UT_OFF_LW + UT_THREADS * 4, UT_OFF_IT = UT_OFF_LS + UT_THREADS * 4,
               UT_OFF_WC = UT_OFF_IT + UT_THREADS * 2, UT_SMEM = UT_OFF_WC + 64;
 
 __device__ __forceinline__ int ut_find(int *P, int n)
@@ -335,10 +338,10 @@ __device__ __forceinline__ void ut_union(int *P, int a, int b)
 }
 
 template <bool REENTRY>
-__global__ void __launch_bounds__(UT_THREADS) k_uf_tile(const B2cHystParams p)
+__global__ void __launch_bounds__(UT_THREADS) k_uf_tile(const B2cHystParams p, uint32_t *blist, int *bcount, const int bcap)
 {
   B2C_DYN_SMEM(smem);
-  int *LP = reinterpret_cast<int *>(smem);                                   // local parents (run heads only), node 0 = strong
+  int *LP = reinterpret_cast<int *>(smem);   // local parents: node 1 + 16 * word + (rank of the run inside its word); 0 = strong
   uint32_t *LW = reinterpret_cast<uint32_t *>(smem + UT_OFF_LW);             // weak words of the tile
   uint32_t *LS = reinterpret_cast<uint32_t *>(smem + UT_OFF_LS);             // strong words of the tile
   uint16_t *IT = reinterpret_cast<uint16_t *>(smem + UT_OFF_IT);             // compacted list: tile positions of the words with weak pixels
@@ -369,13 +372,15 @@ __global__ void __launch_bounds__(UT_THREADS) k_uf_tile(const B2cHystParams p)
     const uint32_t mask = __ballot_sync(B2C_FULL, wd != 0u);
     if (lane == 0) WC[warp] = __popc(mask);
     __syncthreads();
-    int before = 0, total = 0;
+    // prefix over the 8 warp counts: lane w reads count w, two ballot-free shuffles give "before" and the total
+    int cw = lane < UT_THREADS / 32 ? WC[lane] : 0, total = cw, before;
 #pragma unroll
-    for (int w = 0; w < UT_THREADS / 32; ++w) {
-      const int c = WC[w];
-      if (w < warp) before += c;
-      total += c;
+    for (int d = 1; d < UT_THREADS / 32; d <<= 1) {
+      const int v = __shfl_up_sync(B2C_FULL, total, d);
+      if (lane >= d) total += v;
     }
+    before = __shfl_sync(B2C_FULL, total - cw, warp);
+    total = __shfl_sync(B2C_FULL, total, UT_THREADS / 32 - 1);
     if (wd) IT[before + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)tid;
     if (tid == 0) WC[UT_THREADS / 32] = total;
   }
@@ -386,7 +391,7 @@ __global__ void __launch_bounds__(UT_THREADS) k_uf_tile(const B2cHystParams p)
   const bool act = tid < nitems;
   const int t = act ? IT[tid] : 0, ly = t >> 3, lw = t & 7, y = y0 + ly, xw = xw0 + lw;
   const uint32_t wd = act ? LW[t] : 0u;
-  const int lbase = 1 + t * 32;   // local node of bit 0 of this word
+  const int lbase = 1 + t * 16;   // local node of the first run of this word
   if (act) {
     // strong bits of the 3x3 neighbourhood, on words: from the tile copy, or from global memory outside the tile.
     // Rows -1 and h are the ghost rows of the S plane; inside the frame the words are rebuilt from the map (the S
@@ -411,8 +416,20 @@ __global__ void __launch_bounds__(UT_THREADS) k_uf_tile(const B2cHystParams p)
       const uint32_t lo = m & (0u - m);
       const uint32_t run = m & ~(m + lo);   // the run of ones that starts at the lowest set bit
       m &= ~run;
-      const int n = lbase + __ffs((int)lo) - 1;
+      const int n = lbase + uf_run_rank(wd, __ffs((int)lo) - 1);
       LP[n] = (run & near) ? 0 : n;
+    }
+  }
+  {   // words with weak pixels on the tile border have union partners in other tiles: per-frame list for k_uf_border
+      // (one atomic per warp on the frame's own counter: no cross-frame contention)
+    const bool bw = act && (ly == 0 || lw == 0 || lw == UT_WORDS - 1);
+    const uint32_t bm = __ballot_sync(B2C_FULL, bw);
+    if (bm) {
+      const int leader = __ffs((int)bm) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(bcount + f, __popc(bm));
+      base = __shfl_sync(B2C_FULL, base, leader);
+      if (bw) blist[(long long)f * bcap + base + __popc(bm & ((1u << lane) - 1u))] = ((uint32_t)y << 10) | (uint32_t)xw;
     }
   }
   __syncthreads();
@@ -429,16 +446,16 @@ __global__ void __launch_bounds__(UT_THREADS) k_uf_tile(const B2cHystParams p)
       const uint32_t lo = m & (0u - m);
       const uint32_t run = m & ~(m + lo);
       m &= ~run;
-      const int n = lbase + __ffs((int)lo) - 1;
-      if ((run & 1u) && (wl >> 31)) ut_union(LP, n, lbase - 32 + uf_run_head(wl, 31));
+      const int n = lbase + uf_run_rank(wd, __ffs((int)lo) - 1);
+      if ((run & 1u) && (wl >> 31)) ut_union(LP, n, lbase - 16 + uf_run_rank(wl, uf_run_head(wl, 31)));
       uint32_t a = (run | (run << 1) | (run >> 1)) & wu;
       while (a) {
         const uint32_t lo2 = a & (0u - a);
         a &= (a + lo2);
-        ut_union(LP, n, lbase - UT_WORDS * 32 + uf_run_head(wu, __ffs((int)lo2) - 1));
+        ut_union(LP, n, lbase - UT_WORDS * 16 + uf_run_rank(wu, uf_run_head(wu, __ffs((int)lo2) - 1)));
       }
-      if ((run & 1u) && (wul >> 31)) ut_union(LP, n, lbase - UT_WORDS * 32 - 32 + uf_run_head(wul, 31));
-      if ((run >> 31) && (wur & 1u)) ut_union(LP, n, lbase - UT_WORDS * 32 + 32);
+      if ((run & 1u) && (wul >> 31)) ut_union(LP, n, lbase - UT_WORDS * 16 - 16 + uf_run_rank(wul, uf_run_head(wul, 31)));
+      if ((run >> 31) && (wur & 1u)) ut_union(LP, n, lbase - UT_WORDS * 16 + 16);   // bit 0 starts the first run
     }
   }
   __syncthreads();
@@ -452,7 +469,7 @@ __global__ void __launch_bounds__(UT_THREADS) k_uf_tile(const B2cHystParams p)
       const uint32_t run = m & ~(m + lo);
       m &= ~run;
       const int hb = __ffs((int)lo) - 1;
-      int r = lbase + hb;
+      int r = lbase + uf_run_rank(wd, hb);
       for (;;) {   // plain walk: the local trees are final now
         const int pr = LP[r];
         if (pr == r || pr == 0) { r = pr; break; }
@@ -460,36 +477,40 @@ __global__ void __launch_bounds__(UT_THREADS) k_uf_tile(const B2cHystParams p)
       }
       int val = 0;
       if (r != 0) {
-        const int q = r - 1;   // local pixel index: (row * 8 + word) * 32 + bit
-        val = (y0 + (q >> 8)) * W32 + xw0 * 32 + (q & 255) + 1;
+        const int q = r - 1, tw = q >> 4;             // root = run number (q & 15) of tile word tw
+        uint32_t st = LW[tw] & ~(LW[tw] << 1);        // its run starts
+        for (int k = q & 15; k > 0; --k) st &= st - 1u;
+        val = (y0 + (tw >> 3)) * W32 + (xw0 + (tw & 7)) * 32 + __ffs((int)st);   // global node = pixel index + 1
       }
       P[gbase + hb] = val;
     }
   }
 }
 
-// unions across tile borders (everything k_uf_tile could not see); one thread per plane word
-__global__ void __launch_bounds__(UFK_THREADS) k_uf_border(const B2cHystParams p)
+// unions across tile borders (everything k_uf_tile could not see), from the per-frame lists written by k_uf_tile.
+// Grid: x = blocks over a frame's list, z = frame.
+__global__ void __launch_bounds__(UFK_THREADS) k_uf_border(const B2cHystParams p, const uint32_t *blist, const int *bcount, const int bcap)
 {
-  const int wpr = (p.w + 31) >> 5, W32 = p.plane_pitch * 32;
-  const long long nwords = (long long)p.nframes * p.h * wpr;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (long long)gridDim.x * blockDim.x) {
-    const int row_ = (int)(i / wpr), xw = (int)(i - (long long)row_ * wpr), f = row_ / p.h, y = row_ - f * p.h;
+  const int f = blockIdx.z, n = bcount[f], W32 = p.plane_pitch * 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t e = blist[(long long)f * bcap + i];
+    const int y = (int)(e >> 10), xw = (int)(e & 1023u);
     const bool top = (y % UT_ROWS) == 0, left = (xw % UT_WORDS) == 0, right = (xw % UT_WORDS) == UT_WORDS - 1;
-    if (top || left || right) uf_union_word(p, f, y, xw, W32, left, top, top || left, top || right);
+    uf_union_word(p, f, y, xw, W32, left, top, top || left, top || right);
   }
 }
 
 // a run survives iff its root is node 0; then (EXPAND) the final S word goes out as 32 bytes of the u8 {0,255} edge map.
 // One thread per plane word.
 template <bool EXPAND>
-__global__ void __launch_bounds__(UFK_THREADS) k_uf_resolve(const B2cHystParams p)
+__global__ void __launch_bounds__(UFK_THREADS) k_uf_resolve(const B2cHystParams p, int *bcount)
 {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) bcount[blockIdx.z] = 0;   // the border list of this frame is consumed
+  // block = (blockDim.x words) x (blockDim.y rows); grid: x = word blocks of a row, y = row blocks, z = frame
   const int wpr = (p.w + 31) >> 5, W32 = p.plane_pitch * 32;
-  const long long nwords = (long long)p.nframes * p.h * wpr;
   bool changed = false;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (long long)gridDim.x * blockDim.x) {
-    const int row_ = (int)(i / wpr), xw = (int)(i - (long long)row_ * wpr), f = row_ / p.h, y = row_ - f * p.h;
+  const int xw = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, f = blockIdx.z;
+  if (xw < wpr && y < p.h) {
     const long long o = f * p.plane_frame_stride + (long long)y * p.plane_pitch + xw;
     uint32_t s = p.S[o];
     uint32_t m = p.C[o] & ~s;
@@ -530,7 +551,7 @@ __global__ void __launch_bounds__(UFK_THREADS) k_uf_resolve(const B2cHystParams 
   }
   // one plain store per warp at most, and only while the flag is still clear (a same-address atomic per thread
   // serialises in L2 and cost more than the whole phase)
-  if (__any_sync(B2C_FULL, changed) && (threadIdx.x & 31) == 0 && __ldcg(p.flags + 4) == 0) __stcg(p.flags + 4, 1);
+  if (changed && __ldcg(p.flags + 4) == 0) __stcg(p.flags + 4, 1);
 }
 
 // expand: S plane -> u8 {0,255}; one thread per 16 pixels (one 128-bit store)

@@ -89,12 +89,19 @@ __attribute__((visibility("default"))) int emu_hysteresis(const uint32_t *map2, 
   else {   // tile_rows < 0: union-find as four launches; ghost rows given => re-entry on planes built by a first pass
     const int reps = (ghost_top || ghost_bot) ? 2 : 1;   // second repetition exercises the REENTRY build on the retained planes
     const dim3 gt((wpr + b2c::UT_WORDS - 1) / b2c::UT_WORDS, (h + b2c::UT_ROWS - 1) / b2c::UT_ROWS, nframes);
+    const int bcap = (int)gt.y * wpr + 2 * (int)gt.x * h;
+    std::vector<uint32_t> bl((size_t)nframes * bcap + 1);
+    std::vector<int> bc(nframes, 0);
+    uint32_t *blp = bl.data();
+    int *bcp = bc.data();
     for (int rep = 0; rep < reps; ++rep) {
-      if (rep == 0) emu::launch(gt, dim3(b2c::UT_THREADS), b2c::UT_SMEM, false, [p] { b2c::k_uf_tile<false>(p); });
-      else emu::launch(gt, dim3(b2c::UT_THREADS), b2c::UT_SMEM, false, [p] { b2c::k_uf_tile<true>(p); });
-      emu::launch(dim3(grid_blocks), dim3(b2c::UFK_THREADS), 0, false, [p] { b2c::k_uf_border(p); });
-      if (rep + 1 < reps) emu::launch(dim3(grid_blocks), dim3(b2c::UFK_THREADS), 0, false, [p] { b2c::k_uf_resolve<false>(p); });
-      else emu::launch(dim3(grid_blocks), dim3(b2c::UFK_THREADS), 0, false, [p] { b2c::k_uf_resolve<true>(p); });
+      if (rep == 0) emu::launch(gt, dim3(b2c::UT_THREADS), b2c::UT_SMEM, false, [=] { b2c::k_uf_tile<false>(p, blp, bcp, bcap); });
+      else emu::launch(gt, dim3(b2c::UT_THREADS), b2c::UT_SMEM, false, [=] { b2c::k_uf_tile<true>(p, blp, bcp, bcap); });
+      emu::launch(dim3(2, 1, nframes), dim3(b2c::UFK_THREADS), 0, false, [=] { b2c::k_uf_border(p, blp, bcp, bcap); });
+      const int tx = 32, ty = 4;
+      const dim3 gr((wpr + tx - 1) / tx, (h + ty - 1) / ty, nframes), br(tx, ty);
+      if (rep + 1 < reps) emu::launch(gr, br, 0, false, [=] { b2c::k_uf_resolve<false>(p, bcp); });
+      else emu::launch(gr, br, 0, false, [=] { b2c::k_uf_resolve<true>(p, bcp); });
     }
   }
   if (bits_out)
