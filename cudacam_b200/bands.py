@@ -74,7 +74,17 @@ class CudaBandBackend:
         _lib.check(_lib.lib.b2c_band_stencil(self._h, ptr, self.row_stride, self._stream()), self._h, "b2c_band_stencil")
 
     def hysteresis(self, first, write_edges):
-        _lib.check(_lib.lib.b2c_band_hysteresis(self._h, 1 if first else 0, 1 if write_edges else 0, None, self._stream()), self._h, "b2c_band_hysteresis")
+        """write_edges: False = bit plane only, True = also the u8 map, "only" = just expand the final bit plane."""
+        we = 2 if write_edges == "only" else 1 if write_edges else 0
+        _lib.check(_lib.lib.b2c_band_hysteresis(self._h, 1 if first else 0, we, None, self._stream()), self._h, "b2c_band_hysteresis")
+
+    def seeded(self):
+        """int32[1] device tensor: 1 if the last re-entry call found a ghost pixel that seeded something new."""
+        if "flag" not in self._views:
+            p = C.c_void_p()
+            _lib.check(_lib.lib.b2c_band_flag_ptr(self._h, C.byref(p)), self._h, "flag")
+            self._views["flag"] = self.torch.as_tensor(_DevArray(p.value, 1, "<i4"), device=f"cuda:{self.device}")
+        return self._views["flag"]
 
     def _view(self, kind, which):
         key = (kind, which)
@@ -136,21 +146,21 @@ class BandCanny:
         b.ghost(1).zero_()
         self.exchange_input_halos()
         b.stencil()
-        first, rounds = True, 0
-        while True:
-            last = False
-            b.hysteresis(first, write_edges=False)
-            first = False
-            rounds += 1
-            if self.world == 1:
-                break
-            old_up, old_down = b.ghost(0).clone(), b.ghost(1).clone()
+        b.hysteresis(True, write_edges=False)   # band-local fixpoint (planes + union-find forest are kept)
+        rounds = 1
+        while self.world > 1:
+            # boundary rows of the edge bit-plane -> the neighbours' ghost rows; re-entry seeds the weak runs that
+            # touch a strong ghost pixel and resolves their components; stop when no rank was seeded anything new.
+            # (One all_gather of rows + flag per round instead of send/recv + all_reduce was measured SLOWER: the
+            # extra small tensor ops on the host cost more than the second NCCL launch.)
             self._exchange(b.boundary(0), b.ghost(0), b.boundary(1), b.ghost(1))
-            changed = ((b.ghost(0) != old_up).any() | (b.ghost(1) != old_down).any()).to(b.ghost(0).dtype).reshape(1)
-            d.all_reduce(changed, op=d.ReduceOp.MAX, group=self.group)
-            if int(changed.item()) == 0:
+            b.hysteresis(False, write_edges=False)
+            flag = b.seeded().clone()
+            d.all_reduce(flag, op=d.ReduceOp.MAX, group=self.group)
+            if int(flag.item()) == 0:
                 break
-        b.hysteresis(False, write_edges=True)   # nothing left to resolve: this pass only expands the bit-plane to u8
+            rounds += 1
+        b.hysteresis(False, write_edges="only")   # the bit plane is final: expand it to the u8 edge map
         self.rounds = rounds
         return rounds
 
@@ -172,28 +182,25 @@ def run_local(backends):
         b.sync()
     for b in backends:
         b.stencil()
-    first, rounds = True, 0
-    while True:
-        for b in backends:
-            b.hysteresis(first, write_edges=False)
+    for b in backends:
+        b.hysteresis(True, write_edges=False)
+    rounds = 1
+    while n > 1:
         for b in backends:
             b.sync()
-        first = False
-        rounds += 1
-        if n == 1:
-            break
-        changed = False
         for i in range(n - 1):
             up, dn = backends[i], backends[i + 1]
-            new_dn_ghost = up.boundary(1).to(dn.ghost(0).device)
-            new_up_ghost = dn.boundary(0).to(up.ghost(1).device)
-            changed |= bool((new_dn_ghost != dn.ghost(0)).any().item()) or bool((new_up_ghost != up.ghost(1)).any().item())
-            dn.ghost(0).copy_(new_dn_ghost)
-            up.ghost(1).copy_(new_up_ghost)
-        if not changed:
+            dn.ghost(0).copy_(up.boundary(1))
+            up.ghost(1).copy_(dn.boundary(0))
+        for b in backends:
+            b.sync()
+        for b in backends:
+            b.hysteresis(False, write_edges=False)
+        if not any(bool(b.seeded().item()) for b in backends):
             break
+        rounds += 1
     for b in backends:
-        b.hysteresis(False, write_edges=True)
+        b.hysteresis(False, write_edges="only")
     for b in backends:
         b.sync()
     return rounds

@@ -200,8 +200,7 @@ int alloc_common(b2c_ctx *c)
     return B2C_ERR_CUDA;
   }
   c->uf_grid = c->sm_count * per_sm;
-  CK(c, cudaFuncSetAttribute(b2c::k_uf_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2c::UT_SMEM));
-  CK(c, cudaFuncSetAttribute(b2c::k_uf_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2c::UT_SMEM));
+  CK(c, cudaFuncSetAttribute(b2c::k_uf_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, b2c::UT_SMEM));
   CK(c, cudaFuncSetAttribute(b2c::k_stencil_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2c::TILE_SMEM));
   CK(c, cudaFuncSetAttribute(b2c::k_stencil_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2c::TILE_SMEM));
   if (b2c::march_configure() != cudaSuccess) return set_err(c, cudaGetLastError(), "march_configure");
@@ -311,17 +310,25 @@ int launch_hysteresis(b2c_ctx *c, int n, uint8_t *edges, size_t edges_pitch, siz
   p.parent_frame_stride = (long long)c->rows_alloc * c->plane_pitch * 32;
   void *args[] = { &p };
   if (c->hyst_impl == 0 && c->wpr <= 1024) {   // (list entries hold the word index in 10 bits: wider images take the cooperative kernel)
-    // union-find as four ordinary launches (build, union, resolve, expand) -- no barrier inside, no host round trip between
+    // union-find as three ordinary launches (tile, border, resolve+expand; row-band re-entry: seed, resolve) -- no
+    // barrier inside, no host round trip between
     const dim3 gt((c->wpr + b2c::UT_WORDS - 1) / b2c::UT_WORDS, (c->rows_alloc + b2c::UT_ROWS - 1) / b2c::UT_ROWS, n);
     const bool pt = c->hyst_phase_timing;
     if (pt) cudaEventRecord(c->ev_h[0], st);
-    if (skip_init) b2c::k_uf_tile<true><<<gt, b2c::UT_THREADS, b2c::UT_SMEM, st>>>(p, c->d_blist, c->d_bcount, c->bcap);
-    else b2c::k_uf_tile<false><<<gt, b2c::UT_THREADS, b2c::UT_SMEM, st>>>(p, c->d_blist, c->d_bcount, c->bcap);
+    const int T = b2c::UFK_THREADS;
+    if (skip_init) {   // row-band re-entry: seeds from the ghost rows on the retained forest
+      b2c::k_uf_seed<<<dim3((c->wpr + T - 1) / T, 2, n), T, 0, st>>>(p);
+    } else {
+      b2c::k_uf_tile<<<gt, b2c::UT_THREADS, b2c::UT_SMEM, st>>>(p, c->d_blist, c->d_bcount, c->bcap);
+    }
     if (pt) cudaEventRecord(c->ev_h[1], st);
     {
       // border list: typically ~12 % of bcap entries; a quarter of the worst case in blocks, grid-stride for the rest
-      const int T = b2c::UFK_THREADS, gb = std::max(1, (c->bcap / 4 + T - 1) / T);
-      b2c::k_uf_border<<<dim3(gb, 1, n), T, 0, st>>>(p, c->d_blist, c->d_bcount, c->bcap);
+      const int gb = std::max(1, (c->bcap / 4 + T - 1) / T);
+      if (!skip_init) {
+        b2c::k_uf_border<<<dim3(gb, 1, n), T, 0, st>>>(p, c->d_blist, c->d_bcount, c->bcap);
+        c->launches++;
+      }
       if (pt) cudaEventRecord(c->ev_h[2], st);
       const int tx = c->wpr >= 256 ? 256 : c->wpr > 32 ? 64 : 32, ty = 256 / tx;   // 256 threads = tx words x ty rows
       const dim3 gr((c->wpr + tx - 1) / tx, (c->rows_alloc + ty - 1) / ty, n), br(tx, ty);
@@ -329,7 +336,7 @@ int launch_hysteresis(b2c_ctx *c, int n, uint8_t *edges, size_t edges_pitch, siz
       else b2c::k_uf_resolve<false><<<gr, br, 0, st>>>(p, c->d_bcount);
       if (pt) cudaEventRecord(c->ev_h[3], st);
     }
-    c->launches += 2;
+    c->launches += 1;   // (+1 at the end of the function: tile / seed and resolve)
     CK(c, cudaGetLastError());
   } else if (c->hyst_impl != 1) {
     // one warp per plane row, at most one full wave of CTAs
@@ -340,6 +347,29 @@ int launch_hysteresis(b2c_ctx *c, int n, uint8_t *edges, size_t edges_pitch, siz
   } else {
     CK(c, cudaLaunchCooperativeKernel((const void *)b2c::k_hysteresis, dim3(c->hyst_grid), dim3(b2c::HYST_THREADS), args, (size_t)c->hyst_smem, st));
   }
+  c->launches++;
+  return B2C_OK;
+}
+
+// S plane -> u8 {0,255} edge map, nothing else
+int launch_expand(b2c_ctx *c, int n, uint8_t *edges, size_t edges_pitch, size_t edges_frame_stride, cudaStream_t st)
+{
+  B2cHystParams p;
+  memset(&p, 0, sizeof(p));
+  p.S = S0(c);
+  p.C = C0(c);
+  p.plane_pitch = c->plane_pitch;
+  p.plane_frame_stride = plane_frame_stride(c);
+  p.w = c->w;
+  p.h = c->rows_alloc;
+  p.nframes = n;
+  p.edges = edges;
+  p.edges_pitch = (long long)edges_pitch;
+  p.edges_frame_stride = (long long)edges_frame_stride;
+  const long long groups = (long long)n * c->rows_alloc * ((c->w + 15) / 16);
+  const unsigned ge = (unsigned)std::max<long long>(1, std::min<long long>((groups + b2c::UFK_THREADS - 1) / b2c::UFK_THREADS, (long long)c->sm_count * 32));
+  b2c::k_uf_expand<<<ge, b2c::UFK_THREADS, 0, st>>>(p);
+  CK(c, cudaGetLastError());
   c->launches++;
   return B2C_OK;
 }
@@ -848,7 +878,16 @@ int b2c_band_hysteresis(b2c_handle c, int first_call, int write_edges, int *chan
   if (!c || !c->band) return B2C_ERR_INVALID;
   DevGuard g(c->dev);
   cudaStream_t st = stream ? (cudaStream_t)stream : c->s_main;
-  int rc = launch_hysteresis(c, 1, c->d_edges, c->edges_pitch, c->edges_frame_stride, first_call ? 0 : 1, write_edges ? 0 : 1, st);
+  int rc;
+  if (write_edges == 2) {   // the bit plane is final: only expand it to the u8 edge map
+    rc = launch_expand(c, 1, c->d_edges, c->edges_pitch, c->edges_frame_stride, st);
+  } else {
+    if (!first_call) CK(c, cudaMemsetAsync(c->d_flags + 6, 0, sizeof(int), st));
+    rc = launch_hysteresis(c, 1, c->d_edges, c->edges_pitch, c->edges_frame_stride, first_call ? 0 : 1, write_edges ? 0 : 1, st);
+    // the cooperative kernels report "an edge bit was added" in flags[4]: same meaning at the fixpoint
+    if (rc == B2C_OK && !first_call && (c->hyst_impl != 0 || c->wpr > 1024))
+      CK(c, cudaMemcpyAsync(c->d_flags + 6, c->d_flags + 4, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  }
   if (rc != B2C_OK) return rc;
   if (changed) {
     CK(c, cudaMemcpyAsync(c->h_flags, c->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -875,7 +914,7 @@ int b2c_band_ghost_ptr(b2c_handle c, int which, void **dev_ptr, int *words)
 int b2c_band_flag_ptr(b2c_handle c, void **dev_ptr)
 {
   if (!c || !dev_ptr) return B2C_ERR_INVALID;
-  *dev_ptr = c->d_flags + 4;
+  *dev_ptr = c->d_flags + 6;
   return B2C_OK;
 }
 

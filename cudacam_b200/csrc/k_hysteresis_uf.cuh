@@ -337,7 +337,6 @@ __device__ __forceinline__ void ut_union(int *P, int a, int b)
   }
 }
 
-template <bool REENTRY>
 __global__ void __launch_bounds__(UT_THREADS) k_uf_tile(const B2cHystParams p, uint32_t *blist, int *bcount, const int bcap)
 {
   B2C_DYN_SMEM(smem);
@@ -355,17 +354,12 @@ __global__ void __launch_bounds__(UT_THREADS) k_uf_tile(const B2cHystParams p, u
     uint32_t wd = 0u, sM = 0u;
     if (y < p.h && xw < wpr) {
       const long long o = f * p.plane_frame_stride + (long long)y * p.plane_pitch + xw;
-      if (REENTRY) {
-        sM = p.S[o];
-        wd = p.C[o] & ~sM;
-      } else {
-        const uint32_t *mrow = p.map2 + f * p.map_frame_stride + (long long)y * p.map_pitch;
-        const uint32_t m0 = mrow[2 * xw], m1 = (2 * xw + 1 < p.map_pitch) ? mrow[2 * xw + 1] : 0u;
-        sM = (m0 & 0xFFFFu) | (m1 << 16);
-        wd = (m0 >> 16) | (m1 & 0xFFFF0000u);
-        p.S[o] = sM;
-        p.C[o] = sM | wd;
-      }
+      const uint32_t *mrow = p.map2 + f * p.map_frame_stride + (long long)y * p.map_pitch;
+      const uint32_t m0 = mrow[2 * xw], m1 = (2 * xw + 1 < p.map_pitch) ? mrow[2 * xw + 1] : 0u;
+      sM = (m0 & 0xFFFFu) | (m1 << 16);
+      wd = (m0 >> 16) | (m1 & 0xFFFF0000u);
+      p.S[o] = sM;
+      p.C[o] = sM | wd;
     }
     LW[tid] = wd;
     LS[tid] = sM;
@@ -402,7 +396,7 @@ __global__ void __launch_bounds__(UT_THREADS) k_uf_tile(const B2cHystParams p, u
       const int l2 = ly + dy, w2 = lw + dx, x2 = xw + dx, yy = y + dy;
       if (x2 < 0 || x2 >= wpr) return 0u;
       if (l2 >= 0 && l2 < UT_ROWS && yy < p.h && w2 >= 0 && w2 < UT_WORDS) return LS[l2 * UT_WORDS + w2];   // (row h is a ghost row: global)
-      if (REENTRY || yy < 0 || yy >= p.h) return __ldcg(Sr + (long long)dy * pp + dx);
+      if (yy < 0 || yy >= p.h) return __ldcg(Sr + (long long)dy * pp + dx);
       const uint32_t *mr = p.map2 + f * p.map_frame_stride + (long long)yy * p.map_pitch;
       const uint32_t a = mr[2 * x2], b = (2 * x2 + 1 < p.map_pitch) ? mr[2 * x2 + 1] : 0u;
       return (a & 0xFFFFu) | (b << 16);
@@ -497,6 +491,41 @@ __global__ void __launch_bounds__(UFK_THREADS) k_uf_border(const B2cHystParams p
     const int y = (int)(e >> 10), xw = (int)(e & 1023u);
     const bool top = (y % UT_ROWS) == 0, left = (xw % UT_WORDS) == 0, right = (xw % UT_WORDS) == UT_WORDS - 1;
     uf_union_word(p, f, y, xw, W32, left, top, top || left, top || right);
+  }
+}
+
+// Row-band mode, rounds after the first: the planes and the union-find forest of the band are still valid (a run is
+// promoted as a whole or not at all), only the ghost rows have gained strong bits.  Every weak run of the first / last
+// band row that touches one of them hangs its root under node 0; k_uf_resolve then promotes the components.
+// Grid: x = blocks of words, y = 0 (first row, ghost row -1) / 1 (last row, ghost row h).
+__global__ void __launch_bounds__(UFK_THREADS) k_uf_seed(const B2cHystParams p)
+{
+  const int wpr = (p.w + 31) >> 5, W32 = p.plane_pitch * 32, pp = p.plane_pitch;
+  const int xw = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.z;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) { p.flags[3] += 1; p.flags[4] = 0; }   // flags[6] ("a new seed arrived") is cleared by the host side before the launch
+  if (xw >= wpr) return;
+  const int y = blockIdx.y ? p.h - 1 : 0, yg = blockIdx.y ? p.h : -1;
+  const long long o = f * p.plane_frame_stride + (long long)y * pp + xw;
+  const uint32_t wd = p.C[o] & ~p.S[o];
+  if (wd == 0u) return;
+  const uint32_t *G = p.S + f * p.plane_frame_stride + (long long)yg * pp + xw;
+  const uint32_t g = __ldcg(G), gl = xw > 0 ? __ldcg(G - 1) : 0u, gr = xw + 1 < wpr ? __ldcg(G + 1) : 0u;
+  const uint32_t near = wd & (g | (g << 1) | (g >> 1) | (gl >> 31) | (gr << 31));
+  if (near == 0u) return;
+  int *P = p.parent + f * p.parent_frame_stride;
+  const int base = y * W32 + xw * 32 + 1;
+  uint32_t m = wd;
+  while (m) {
+    const uint32_t lo = m & (0u - m);
+    const uint32_t run = m & ~(m + lo);
+    m &= ~run;
+    if (run & near) {
+      const int r = uf_find(P, base + __ffs((int)lo) - 1);
+      if (r != 0) {
+        atomicMin(P + r - 1, 0);
+        if (__ldcg(p.flags + 6) == 0) __stcg(p.flags + 6, 1);   // this band has something new to resolve (and maybe to pass on)
+      }
+    }
   }
 }
 

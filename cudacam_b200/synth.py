@@ -33,21 +33,25 @@ def batch(kind, n, w, h, stream=0, distinct=None):
 
 
 _GIGA_TILE = 4096
+_GIGA_PITCH = 3960   # mosaic pitch: NOT a divisor of the band heights (16384 / 2, 4, 8), so that the hard tile-to-tile
+                     # edges of the mosaic do not lie exactly on the band seams (a picture-wide edge ON a seam makes
+                     # every weak chain along it cross the seam again and again: 25 global rounds instead of 3)
 
 
 def giga_rows(y0, y1, w=16384, h=16384):
-    """Rows [y0, y1) of the synthetic gigapixel image of BASELINE config 5: a mosaic of four distinct 4096x4096
-    'scene' tiles (tile (ty, tx) uses picture (ty + tx) % 4), cropped to w x h.  Returns (y1-y0, w, 3) uint8."""
-    T = _GIGA_TILE
+    """Rows [y0, y1) of the synthetic gigapixel image of BASELINE config 5: a mosaic of four distinct 'scene'
+    pictures (tile (ty, tx) shows picture (ty + tx) % 4) at a pitch of 3960 pixels, cropped to w x h.
+    Returns (y1-y0, w, 3) uint8."""
+    T, Pt = _GIGA_TILE, _GIGA_PITCH
     tiles = {}
     out = np.empty((y1 - y0, w, 3), np.uint8)
     for y in range(y0, y1):
-        ty, ry = divmod(y, T)
-        for tx in range((w + T - 1) // T):
+        ty, ry = divmod(y, Pt)
+        for tx in range((w + Pt - 1) // Pt):
             k = (ty + tx) % 4
             if k not in tiles:
                 tiles[k] = frame("scene", stream_seed(1000, k), T, T)
-            x0 = tx * T
-            n = min(T, w - x0)
+            x0 = tx * Pt
+            n = min(Pt, w - x0)
             out[y - y0, x0:x0 + n] = tiles[k][ry, :n]
     return out

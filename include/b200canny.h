@@ -126,13 +126,18 @@ B2C_API void *b2c_stream(b2c_handle h);
  * reference's zero padding only outside the global image. */
 B2C_API int b2c_create_band(b2c_handle *out, int device, int width, int band_rows, int y0, int height_global);
 B2C_API int b2c_band_stencil(b2c_handle h, const uint8_t *dev_bgr_band_row0, size_t row_stride, void *stream);
-/* local hysteresis to a fixpoint given the current ghost rows; *changed = 1 if any S bit was added */
+/* Band-local hysteresis to a fixpoint given the current ghost rows.  first_call != 0: planes and union-find forest
+ * from the 2-bit map (3 launches); first_call == 0: re-entry -- the forest is kept, the weak runs of the first / last
+ * row that touch a strong ghost pixel are seeded and the components resolved (2 launches).  write_edges: 0 = bit plane
+ * only, 1 = also expand to the u8 edge map, 2 = ONLY expand the (final) bit plane.  *changed (may be null; a non-null
+ * pointer makes the call blocking) = 1 if any edge bit was added. */
 B2C_API int b2c_band_hysteresis(b2c_handle h, int first_call, int write_edges, int *changed, void *stream);
 /* boundary rows of the S plane: which = 0 first band row, 1 last band row (to send);
  * ghost rows: which = 0 row above the band, 1 row below (to receive).  words = ceil(w/32). */
 B2C_API int b2c_band_boundary_ptr(b2c_handle h, int which, void **dev_ptr, int *words);
 B2C_API int b2c_band_ghost_ptr(b2c_handle h, int which, void **dev_ptr, int *words);
-/* device int that is 1 after b2c_band_hysteresis if that call added any edge bit (for a device-side all-reduce) */
+/* device int that is 1 after a re-entry call of b2c_band_hysteresis if a ghost row seeded anything new in this band
+ * (cleared at the start of every re-entry call); the row-band driver all-reduces it to detect the global fixpoint */
 B2C_API int b2c_band_flag_ptr(b2c_handle h, void **dev_ptr);
 
 /* ---- misc */

@@ -95,9 +95,24 @@ __attribute__((visibility("default"))) int emu_hysteresis(const uint32_t *map2, 
     uint32_t *blp = bl.data();
     int *bcp = bc.data();
     for (int rep = 0; rep < reps; ++rep) {
-      if (rep == 0) emu::launch(gt, dim3(b2c::UT_THREADS), b2c::UT_SMEM, false, [=] { b2c::k_uf_tile<false>(p, blp, bcp, bcap); });
-      else emu::launch(gt, dim3(b2c::UT_THREADS), b2c::UT_SMEM, false, [=] { b2c::k_uf_tile<true>(p, blp, bcp, bcap); });
-      emu::launch(dim3(2, 1, nframes), dim3(b2c::UFK_THREADS), 0, false, [=] { b2c::k_uf_border(p, blp, bcp, bcap); });
+      if (rep == 0) {
+        // first pass WITHOUT the ghost rows when a re-entry follows (they arrive later in row-band mode)
+        std::vector<uint32_t> keep_top, keep_bot;
+        if (reps == 2) {
+          keep_top.assign(S.begin(), S.begin() + pitch);
+          keep_bot.assign(S.begin() + (size_t)(h + 1) * pitch, S.begin() + (size_t)(h + 2) * pitch);
+          std::fill(S.begin(), S.begin() + pitch, 0u);
+          std::fill(S.begin() + (size_t)(h + 1) * pitch, S.begin() + (size_t)(h + 2) * pitch, 0u);
+        }
+        emu::launch(gt, dim3(b2c::UT_THREADS), b2c::UT_SMEM, false, [=] { b2c::k_uf_tile(p, blp, bcp, bcap); });
+        emu::launch(dim3(2, 1, nframes), dim3(b2c::UFK_THREADS), 0, false, [=] { b2c::k_uf_border(p, blp, bcp, bcap); });
+        if (reps == 2) {
+          std::copy(keep_top.begin(), keep_top.end(), S.begin());
+          std::copy(keep_bot.begin(), keep_bot.end(), S.begin() + (size_t)(h + 1) * pitch);
+        }
+      } else {
+        emu::launch(dim3((wpr + b2c::UFK_THREADS - 1) / b2c::UFK_THREADS, 2, nframes), dim3(b2c::UFK_THREADS), 0, false, [=] { b2c::k_uf_seed(p); });
+      }
       const int tx = 32, ty = 4;
       const dim3 gr((wpr + tx - 1) / tx, (h + ty - 1) / ty, nframes), br(tx, ty);
       if (rep + 1 < reps) emu::launch(gr, br, 0, false, [=] { b2c::k_uf_resolve<false>(p, bcp); });

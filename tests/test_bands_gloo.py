@@ -28,6 +28,8 @@ class EmuBandBackend:
         self._g = [torch.zeros(self.wpr, dtype=torch.int32) for _ in range(2)]
         self._edges = None
         self._map2 = None
+        self._bits = None
+        self._seeded = torch.zeros(1, dtype=torch.int32)
         self._override = thresh_override   # (rows, w) u8 {0,128,255}: skips the stencil (hysteresis-only tests)
 
     def input_rows(self, r0, r1):
@@ -50,14 +52,22 @@ class EmuBandBackend:
             self._map2 = E.stencil(f, impl=1, y0=self.y0, h_glob=self.height_global, rows=self.rows, row0=bands.HALO)["map2"][0]
 
     def hysteresis(self, first, write_edges):
-        # the emulator entry rebuilds the planes from the 2-bit map on every call; with the ghost rows as extra
-        # seeds that reaches the same fixpoint as the product's re-entry on the retained planes
+        if write_edges == "only":
+            return   # the emulator entry always writes the u8 map
+        # the emulator entry rebuilds the planes from the 2-bit map on every call (first pass without the ghost rows,
+        # then the product's re-entry kernels with them): same fixpoint as re-entering on retained planes
         gt = self._g[0].numpy().view(np.uint32)
         gb = self._g[1].numpy().view(np.uint32)
         edges, bits, _, _ = E.hysteresis(self._map2, self.width, grid_blocks=2, tile_rows=-1, ghost_top=gt, ghost_bot=gb)
+        new = not first and (self._bits is None or not np.array_equal(bits[0], self._bits))
+        self._seeded = torch.tensor([1 if new else 0], dtype=torch.int32)
+        self._bits = bits[0].copy()
         self._edges = edges[0]
         self._b[0].copy_(torch.from_numpy(bits[0][0].view(np.int32).copy()))
         self._b[1].copy_(torch.from_numpy(bits[0][-1].view(np.int32).copy()))
+
+    def seeded(self):
+        return self._seeded
 
     def sync(self):
         pass
