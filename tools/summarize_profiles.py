@@ -3,7 +3,7 @@
   profiles/<tag>_launches.csv          the ncu launch list of `bench.py` (gpu__time_duration per launch) + per-kernel shares
   profiles/<tag>_<kernel>_ncu.txt      key metrics of the --set full capture (time, DRAM bytes, throughputs, stalls, pipes)
   profiles/<tag>_<kernel>_stages.txt   warp-instructions per kernel stage / source line (from the source page)
-  profiles/<tag>_k_stencil_fused.sass  cuobjdump -sass of the shipped kernel
+  profiles/<tag>_k_stencil_march.sass  cuobjdump -sass of the shipped stencil kernel
   profiles/stencil_traffic.json        DRAM bytes per launch of the stencil kernel (bench.py reports it as roofline.traffic)
 usage: tools/summarize_profiles.py [tag]"""
 import collections
@@ -67,9 +67,12 @@ def kernel_summary(name, px=None):
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
     tmp = f"/tmp/{TAG}_{name}_src.csv"
     open(tmp, "w").write(src)
-    a = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_stage_split.py"), tmp] + ([str(px)] if px else []), capture_output=True, text=True).stdout
+    if name == "stencil":
+        a = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_march_stages.py"), rep, str(px)], capture_output=True, text=True).stdout
+    else:
+        a = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_stage_split.py"), tmp] + ([str(px)] if px else []), capture_output=True, text=True).stdout
     b = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_source_summary.py"), tmp, "30"], capture_output=True, text=True).stdout
-    open(os.path.join(P, f"{TAG}_{name}_stages.txt"), "w").write("# regions = code between BAR.SYNC instructions, in SASS address order\n" + a + "\n# per source line\n" + b)
+    open(os.path.join(P, f"{TAG}_{name}_stages.txt"), "w").write("# per kernel stage (stencil: source markers; others: code between BAR.SYNC instructions, in SASS address order)\n" + a + "\n# per source line\n" + b)
     return traffic
 
 
@@ -92,15 +95,19 @@ def launches():
 
 px = 64 * 1920 * 1080
 tr = kernel_summary("stencil", px)
-kernel_summary("hyst", px)
-kernel_summary("hyst4k", 3840 * 2160)
+for k in ("k_uf_tile", "k_uf_border", "k_uf_resolve"):
+    kernel_summary(k, px)
 launches()
 if tr:
     json.dump({"bytes_per_launch_batch1080p": tr, "source": f"profiles/{TAG}_stencil_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"},
               open(os.path.join(P, "stencil_traffic.json"), "w"), indent=1)
 so = os.path.join(ROOT, "cudacam_b200", "libb200canny.so")
-sass = subprocess.run(["cuobjdump", "-sass", "-fun", "k_stencil_fused", so], capture_output=True, text=True).stdout
-if "Function" not in sass:
-    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
-open(os.path.join(P, f"{TAG}_k_stencil_fused.sass"), "w").write(sass)
+allsass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+keep, on = [], False
+for line in allsass.split("\n"):
+    if "Function :" in line:
+        on = "k_stencil_march" in line
+    if on:
+        keep.append(line)
+open(os.path.join(P, f"{TAG}_k_stencil_march.sass"), "w").write("\n".join(keep) + "\n")
 print("profiles written:", sorted(os.listdir(P)))
