@@ -355,6 +355,9 @@ def run_giga(args, wl):
     band_host = synth.giga_rows(y0, y0 + rows, W, Hh)
     be = bands.CudaBandBackend(W, rows, y0, Hh, device=local)
     be.load(band_host)
+    p2p = world > 1 and os.environ.get("B2C_BAND_NCCL", "0") != "1"
+    if p2p:
+        be.enable_p2p(dist, rank, world)   # cross-band rounds on the devices (NVLink peer stores); B2C_BAND_NCCL=1 = NCCL rounds
     bc = bands.BandCanny(be, rank, world, dist if world > 1 else None)
 
     def barrier():
@@ -400,7 +403,7 @@ def run_giga(args, wl):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": wl["desc"], "width": W, "height": Hh, "band_rows_rank0": rows, "thresholds": [10, 40], "global_hysteresis_rounds": rounds,
-                       "l2_policy": "band input (%.0f MB) larger than the 126 MB L2, no flush" % (rows * W * 3 / 1e6), "parallelism": f"row bands x{world}, NCCL halo + boundary rows + 1-int all-reduce per round",
+                       "l2_policy": "band input (%.0f MB) larger than the 126 MB L2, no flush" % (rows * W * 3 / 1e6), "parallelism": f"row bands x{world}, NCCL input halo; hysteresis rounds: " + ("peer-memory stores + device-side convergence flags" if p2p else "NCCL send/recv + 1-int all-reduce per round"),
                        "edge_pixel_fraction_rank0": float((edges == 255).mean())},
             "roofline": {"bound": "hbm", "kernel": "whole step (4 B/pixel end to end: 3 in + 1 out)", "achieved": px * 4.0 / (total_ms / args.steps * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s",
                          "frac": px * 4.0 / (total_ms / args.steps * 1e-3) / 1e9 / world / peak, "traffic": None, "peak_source": which},

@@ -51,6 +51,11 @@ _SIGS = {
     "b2c_band_boundary_ptr": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_i)]),
     "b2c_band_ghost_ptr": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_i)]),
     "b2c_band_flag_ptr": (_i, [_vp, C.POINTER(_vp)]),
+    "b2c_band_p2p_export": (_i, [_vp, _vp]),
+    "b2c_band_p2p_open": (_i, [_vp, _vp, _i, _i]),
+    "b2c_band_p2p_converge": (_i, [_vp, _i, C.POINTER(_i), _vp]),
+    "b2c_band_input": (_i, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
+    "b2c_band_p2p_halo": (_i, [_vp, _vp]),
     "b2c_strerror": (C.c_char_p, [_i]),
     "b2c_last_cuda_error": (C.c_char_p, [_vp]),
     "b2c_version": (C.c_char_p, []),

@@ -32,7 +32,8 @@ class _DevArray:
     """Minimal __cuda_array_interface__ holder so torch can view device memory owned by the C library."""
 
     def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = dict(shape=(n,), typestr=typestr, data=(int(ptr), False), version=3)
+        shape = tuple(n) if isinstance(n, (tuple, list)) else (n,)
+        self.__cuda_array_interface__ = dict(shape=shape, typestr=typestr, data=(int(ptr), False), version=3)
 
 
 class CudaBandBackend:
@@ -45,8 +46,13 @@ class CudaBandBackend:
         h = C.c_void_p()
         _lib.check(_lib.lib.b2c_create_band(C.byref(h), device, width, rows, y0, height_global), what="b2c_create_band")
         self._h = h
-        self.row_stride = (width * 3 + 15) // 16 * 16
-        self.buf = torch.zeros((rows + 2 * HALO, self.row_stride), dtype=torch.uint8, device=f"cuda:{device}")
+        # the input buffer (HALO rows above, the band, HALO rows below) is owned by the C library so that the neighbour
+        # ranks can map it (CUDA IPC) and store their halo rows straight into it
+        p, st = C.c_void_p(), C.c_size_t()
+        _lib.check(_lib.lib.b2c_band_input(h, C.byref(p), C.byref(st)), h, "b2c_band_input")
+        self.row_stride = st.value
+        with torch.cuda.device(device):
+            self.buf = torch.as_tensor(_DevArray(p.value, (rows + 2 * HALO, self.row_stride), "|u1"), device=f"cuda:{device}")
         self.wpr = (width + 31) // 32
         self._views = {}
 
@@ -77,6 +83,26 @@ class CudaBandBackend:
         """write_edges: False = bit plane only, True = also the u8 map, "only" = just expand the final bit plane."""
         we = 2 if write_edges == "only" else 1 if write_edges else 0
         _lib.check(_lib.lib.b2c_band_hysteresis(self._h, 1 if first else 0, we, None, self._stream()), self._h, "b2c_band_hysteresis")
+
+    def enable_p2p(self, dist, rank, world, group=None):
+        """Maps the other ranks' mailboxes (CUDA IPC) so that the cross-band rounds run on the devices (NVLink peer
+        stores, device-side convergence) instead of through NCCL + host.  Ranks must be on one box."""
+        h = (C.c_ubyte * 144)()
+        _lib.check(_lib.lib.b2c_band_p2p_export(self._h, h), self._h, "b2c_band_p2p_export")
+        mine = self.torch.tensor(list(h), dtype=self.torch.uint8, device=f"cuda:{self.device}")
+        allh = self.torch.empty(144 * world, dtype=self.torch.uint8, device=mine.device)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        buf = bytes(allh.cpu().tolist())
+        _lib.check(_lib.lib.b2c_band_p2p_open(self._h, buf, world, rank), self._h, "b2c_band_p2p_open")
+        self.p2p = True
+
+    def halo_p2p(self):
+        _lib.check(_lib.lib.b2c_band_p2p_halo(self._h, self._stream()), self._h, "b2c_band_p2p_halo")
+
+    def converge(self, rounds_per_sync=4):
+        n = C.c_int(0)
+        _lib.check(_lib.lib.b2c_band_p2p_converge(self._h, rounds_per_sync, C.byref(n), self._stream()), self._h, "b2c_band_p2p_converge")
+        return n.value
 
     def seeded(self):
         """int32[1] device tensor: 1 if the last re-entry call found a ghost pixel that seeded something new."""
@@ -136,6 +162,9 @@ class BandCanny:
 
     def exchange_input_halos(self):
         b, n = self.b, self.b.rows
+        if self.world > 1 and getattr(b, "p2p", False):
+            b.halo_p2p()   # peer stores into the neighbours' buffers + device-side arrival counters
+            return
         # contiguous staging: rows of a strided buffer are contiguous blocks already (full-stride rows)
         self._exchange(b.input_rows(HALO, 2 * HALO), b.input_rows(0, HALO), b.input_rows(n, n + HALO), b.input_rows(n + HALO, n + 2 * HALO))
 
@@ -148,7 +177,9 @@ class BandCanny:
         b.stencil()
         b.hysteresis(True, write_edges=False)   # band-local fixpoint (planes + union-find forest are kept)
         rounds = 1
-        while self.world > 1:
+        if self.world > 1 and getattr(b, "p2p", False):
+            rounds = max(1, b.converge() - 1)   # device-side rounds over NVLink peer memory (the last one finds nothing new)
+        while self.world > 1 and not getattr(b, "p2p", False):
             # boundary rows of the edge bit-plane -> the neighbours' ghost rows; re-entry seeds the weak runs that
             # touch a strong ghost pixel and resolves their components; stop when no rank was seeded anything new.
             # (One all_gather of rows + flag per round instead of send/recv + all_reduce was measured SLOWER: the

@@ -23,6 +23,7 @@
 #include "b2c_device.cuh"
 #include "k_hysteresis.cuh"
 #include "k_hysteresis_uf.cuh"
+#include "k_band_p2p.cuh"
 #include "k_stencil_fused.cuh"
 #include "k_stencil_march.cuh"
 #include "k_stencil_tile.cuh"
@@ -95,6 +96,15 @@ struct b2c_ctx {
   // band mode
   bool band = false;
   int band_y0 = 0, h_glob = 0;
+  // band mode, peer-to-peer rounds: own mailbox + control ints, the other ranks' mailboxes mapped through CUDA IPC
+  uint32_t *d_mailbox = nullptr;
+  int *d_p2pctl = nullptr;
+  int *h_p2pctl = nullptr;
+  void *peer_mail[b2c::BP_MAXW] = {};
+  void *peer_in[2] = { nullptr, nullptr };   // band input buffers of the upper / lower neighbour
+  int peer_rows_up = 0;
+  uint8_t *d_band_in = nullptr;            // own band input buffer: 4 halo rows, the band, 4 halo rows
+  int p2p_world = 0, p2p_rank = 0, p2p_run = 0;
 
   int hyst_grid = 0, hyst_smem = 0;
   long long launches = 0;
@@ -475,6 +485,14 @@ void b2c_destroy(b2c_handle c)
   cudaFree(c->d_grad);
   cudaFree(c->d_flags);
   cudaFree(c->d_parent);
+  for (int k = 0; k < c->p2p_world; ++k)
+    if (k != c->p2p_rank && c->peer_mail[k]) cudaIpcCloseMemHandle(c->peer_mail[k]);
+  for (auto &q : c->peer_in)
+    if (q) cudaIpcCloseMemHandle(q);
+  cudaFree(c->d_band_in);
+  cudaFree(c->d_mailbox);
+  cudaFree(c->d_p2pctl);
+  if (c->h_p2pctl) cudaFreeHost(c->h_p2pctl);
   cudaFree(c->d_blist);
   cudaFree(c->d_bcount);
   cudaFree(c->d_zeros);
@@ -895,6 +913,159 @@ int b2c_band_hysteresis(b2c_handle c, int first_call, int write_edges, int *chan
     *changed = c->h_flags[4];
   }
   return B2C_OK;
+}
+
+// ---- peer-to-peer rounds (see k_band_p2p.cuh) -----------------------------------------------------------------
+int b2c_band_input(b2c_handle c, void **dev_ptr, size_t *row_stride)
+{
+  if (!c || !c->band || !dev_ptr) return B2C_ERR_INVALID;
+  DevGuard g(c->dev);
+  const size_t stride = round_up((size_t)c->w * 3, 16);
+  if (!c->d_band_in) {
+    CK(c, cudaMalloc(&c->d_band_in, stride * (c->rows_alloc + 8)));
+    CK(c, cudaMemset(c->d_band_in, 0, stride * (c->rows_alloc + 8)));
+  }
+  *dev_ptr = c->d_band_in;
+  if (row_stride) *row_stride = stride;
+  return B2C_OK;
+}
+
+int b2c_band_p2p_export(b2c_handle c, void *blob_144)
+{
+  if (!c || !c->band || !blob_144) return B2C_ERR_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  DevGuard g(c->dev);
+  if (!c->d_mailbox) {
+    const size_t bytes = b2c::bp_mailbox_words(c->wpr) * sizeof(uint32_t);
+    CK(c, cudaMalloc(&c->d_mailbox, bytes));
+    CK(c, cudaMemset(c->d_mailbox, 0, bytes));
+    CK(c, cudaMalloc(&c->d_p2pctl, 8 * sizeof(int)));
+    CK(c, cudaMemset(c->d_p2pctl, 0, 8 * sizeof(int)));
+    CK(c, cudaMallocHost(&c->h_p2pctl, 8 * sizeof(int)));
+  }
+  void *in;
+  int rc = b2c_band_input(c, &in, nullptr);
+  if (rc != B2C_OK) return rc;
+  cudaIpcMemHandle_t h[2];
+  CK(c, cudaIpcGetMemHandle(&h[0], c->d_mailbox));
+  CK(c, cudaIpcGetMemHandle(&h[1], c->d_band_in));
+  memset(blob_144, 0, 144);
+  memcpy(blob_144, h, 128);
+  const int rows = c->rows_alloc;
+  memcpy((char *)blob_144 + 128, &rows, sizeof(int));
+  return B2C_OK;
+}
+
+int b2c_band_p2p_open(b2c_handle c, const void *all_blobs, int world, int rank)
+{
+  if (!c || !c->band || !all_blobs || !c->d_mailbox || world < 2 || world > b2c::BP_MAXW || rank < 0 || rank >= world) return B2C_ERR_INVALID;
+  DevGuard g(c->dev);
+  for (int k = 0; k < world; ++k) {
+    const char *blob = (const char *)all_blobs + 144 * k;
+    if (k == rank) {
+      c->peer_mail[k] = c->d_mailbox;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, blob, 64);
+    CK(c, cudaIpcOpenMemHandle(&c->peer_mail[k], h, cudaIpcMemLazyEnablePeerAccess));
+    if (k == rank - 1 || k == rank + 1) {
+      memcpy(&h, blob + 64, 64);
+      CK(c, cudaIpcOpenMemHandle(&c->peer_in[k == rank - 1 ? 0 : 1], h, cudaIpcMemLazyEnablePeerAccess));
+      if (k == rank - 1) memcpy(&c->peer_rows_up, blob + 128, sizeof(int));
+    }
+  }
+  c->p2p_world = world;
+  c->p2p_rank = rank;
+  return B2C_OK;
+}
+
+namespace
+{
+void fill_p2p(b2c_ctx *c, b2c::B2cBandP2P &q)
+{
+  memset(&q, 0, sizeof(q));
+  for (int k = 0; k < c->p2p_world; ++k) q.mail[k] = (uint32_t *)c->peer_mail[k];
+  q.world = c->p2p_world;
+  q.rank = c->p2p_rank;
+  q.wpr = c->wpr;
+  q.ctl = c->d_p2pctl;
+  q.in_up = (uint8_t *)c->peer_in[0];
+  q.in_dn = (uint8_t *)c->peer_in[1];
+  q.in_own = c->d_band_in;
+  q.in_stride = (long long)round_up((size_t)c->w * 3, 16);
+  q.rows_own = c->rows_alloc;
+  q.rows_up = c->peer_rows_up;
+  q.row_bytes = c->w * 3;
+}
+}// namespace
+
+// the 4 input rows on either side of every seam, stored straight into the neighbours' band input buffers; returns
+// (asynchronously) once both neighbours' rows have landed in this band's buffer
+int b2c_band_p2p_halo(b2c_handle c, void *stream)
+{
+  if (!c || !c->band || c->p2p_world < 2 || !c->d_band_in) return B2C_ERR_INVALID;
+  DevGuard g(c->dev);
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->s_main;
+  b2c::B2cBandP2P q;
+  fill_p2p(c, q);
+  const int cpr = (c->w * 3 + 15) / 16, nblocks = (4 * cpr + 255) / 256;
+  c->p2p_run += 1;
+  b2c::k_band_push_halo<<<dim3(nblocks, 2), 256, 0, st>>>(q);
+  b2c::k_band_wait_halo<<<1, 1, 0, st>>>(q, c->p2p_run, nblocks);
+  CK(c, cudaGetLastError());
+  c->launches += 2;
+  return B2C_OK;
+}
+
+int b2c_band_p2p_converge(b2c_handle c, int rounds_per_sync, int *rounds_out, void *stream)
+{
+  if (!c || !c->band || c->p2p_world < 2 || rounds_per_sync < 1) return B2C_ERR_INVALID;
+  if (c->hyst_impl != 0 || c->wpr > 1024) return B2C_ERR_UNSUPPORTED;
+  DevGuard g(c->dev);
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->s_main;
+  B2cHystParams p;
+  memset(&p, 0, sizeof(p));
+  p.S = S0(c);
+  p.C = C0(c);
+  p.plane_pitch = c->plane_pitch;
+  p.plane_frame_stride = plane_frame_stride(c);
+  p.w = c->w;
+  p.h = c->rows_alloc;
+  p.nframes = 1;
+  p.flags = c->d_flags;
+  p.parent = c->d_parent;
+  p.parent_frame_stride = (long long)c->rows_alloc * c->plane_pitch * 32;
+  p.skip = c->d_p2pctl + b2c::BP_DONE;
+  p.need = c->d_p2pctl + b2c::BP_SEEDED;   // set by this round's seed kernel iff something new was seeded in this band
+  b2c::B2cBandP2P q;
+  fill_p2p(c, q);
+  // start of a run: not done, no rounds yet, "seeded" forced on so that the first exchange is always evaluated
+  CK(c, cudaMemsetAsync(c->d_p2pctl + b2c::BP_DONE, 0, sizeof(int), st));
+  CK(c, cudaMemsetAsync(c->d_p2pctl + b2c::BP_RUN_ROUNDS, 0, sizeof(int), st));
+  CK(c, cudaMemsetAsync(c->d_p2pctl + b2c::BP_SEEDED, 0, sizeof(int), st));
+  CK(c, cudaMemsetAsync(c->d_p2pctl + b2c::BP_SEEDED, 1, 1, st));
+  const int T = b2c::UFK_THREADS;
+  const int tx = c->wpr >= 256 ? 256 : c->wpr > 32 ? 64 : 32, ty = 256 / tx;
+  const dim3 gr((c->wpr + tx - 1) / tx, (c->rows_alloc + ty - 1) / ty, 1), br(tx, ty);
+  for (int total = 0; total < 4096; total += rounds_per_sync) {
+    for (int k = 0; k < rounds_per_sync; ++k) {
+      b2c::k_band_push<<<1, 256, 0, st>>>(p, q);
+      b2c::k_band_seed<<<dim3((c->wpr + T - 1) / T, 2), T, 0, st>>>(p, q);
+      b2c::k_uf_resolve<false><<<gr, br, 0, st>>>(p, c->d_bcount);
+      c->launches += 3;
+    }
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(c->h_p2pctl, c->d_p2pctl, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    if (c->h_p2pctl[b2c::BP_ERROR]) {
+      c->last_err = "row-band peer-to-peer round timed out waiting for another rank";
+      return B2C_ERR_STATE;
+    }
+    if (c->h_p2pctl[b2c::BP_DONE]) break;
+  }
+  if (rounds_out) *rounds_out = c->h_p2pctl[b2c::BP_RUN_ROUNDS];
+  return c->h_p2pctl[b2c::BP_DONE] ? B2C_OK : B2C_ERR_STATE;
 }
 
 int b2c_band_boundary_ptr(b2c_handle c, int which, void **dev_ptr, int *words)

@@ -534,6 +534,7 @@ __global__ void __launch_bounds__(UFK_THREADS) k_uf_seed(const B2cHystParams p)
 template <bool EXPAND>
 __global__ void __launch_bounds__(UFK_THREADS) k_uf_resolve(const B2cHystParams p, int *bcount)
 {
+  if ((p.skip && __ldcg(p.skip)) || (p.need && __ldcg(p.need) == 0)) return;
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) bcount[blockIdx.z] = 0;   // the border list of this frame is consumed
   // block = (blockDim.x words) x (blockDim.y rows); grid: x = word blocks of a row, y = row blocks, z = frame
   const int wpr = (p.w + 31) >> 5, W32 = p.plane_pitch * 32;

@@ -140,6 +140,24 @@ B2C_API int b2c_band_ghost_ptr(b2c_handle h, int which, void **dev_ptr, int *wor
  * (cleared at the start of every re-entry call); the row-band driver all-reduces it to detect the global fixpoint */
 B2C_API int b2c_band_flag_ptr(b2c_handle h, void **dev_ptr);
 
+/* Peer-to-peer rounds for ranks of ONE box (one process per GPU): instead of NCCL send/recv + all-reduce per round, every
+ * rank maps the other ranks' mailboxes (CUDA IPC) and the rounds run on the device: boundary rows and "seeded" flags
+ * are stored straight into the peers' memory over NVLink, convergence is decided by every rank from the same flags.
+ * b2c_band_p2p_export: 144-byte blob (IPC handles of this band's mailbox and input buffer + its height), to be
+ * all-gathered by the caller; b2c_band_p2p_open: the blobs of all ranks, in rank order;
+ * b2c_band_p2p_converge: after the first b2c_band_hysteresis call -- runs exchange / seed / resolve rounds until the
+ * global fixpoint, reading the device-side done flag once per `rounds_per_sync` rounds; blocking; *rounds_out =
+ * exchange rounds executed.  Follow with b2c_band_hysteresis(h, 0, 2, ...) to expand the final bit plane. */
+B2C_API int b2c_band_p2p_export(b2c_handle h, void *blob_144);
+B2C_API int b2c_band_p2p_open(b2c_handle h, const void *all_blobs, int world, int rank);
+/* the band's input buffer owned by the handle (so that it can be shared with the neighbours): row 0..3 = halo rows
+ * above the band, rows 4..4+band_rows-1 = the band, then 4 halo rows; rows are row_stride bytes apart */
+B2C_API int b2c_band_input(b2c_handle h, void **dev_ptr, size_t *row_stride);
+/* input halo exchange over peer memory: my first / last 4 rows -> the neighbours' buffers; asynchronous on `stream`,
+ * later work on the stream sees both neighbours' rows */
+B2C_API int b2c_band_p2p_halo(b2c_handle h, void *stream);
+B2C_API int b2c_band_p2p_converge(b2c_handle h, int rounds_per_sync, int *rounds_out, void *stream);
+
 /* ---- misc */
 B2C_API const char *b2c_strerror(int status);
 B2C_API const char *b2c_last_cuda_error(b2c_handle h);

@@ -55,7 +55,7 @@ def _free_port():
     return p
 
 
-def _nccl_worker(rank, world, port, w, h, q):
+def _nccl_worker(rank, world, port, w, h, q, p2p):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -66,15 +66,20 @@ def _nccl_worker(rank, world, port, w, h, q):
         y0, rows = bands.band_rows(h, world, rank)
         be = bands.CudaBandBackend(w, rows, y0, h, device=rank)
         be.load(img[y0:y0 + rows])
-        rounds = bands.BandCanny(be, rank, world, dist).run()
+        if p2p:
+            be.enable_p2p(dist, rank, world)
+        bc = bands.BandCanny(be, rank, world, dist)
+        bc.run()
+        rounds = bc.run()   # twice: the second run re-uses planes, forest, mailboxes and round counters
         q.put((rank, y0, rows, rounds, be.edges()))
         be.close()
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("p2p", [False, True], ids=["nccl_rounds", "p2p_rounds"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_nccl_bands_equal_unsharded(world):
+def test_nccl_bands_equal_unsharded(world, p2p):
     if _ndev() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
@@ -82,7 +87,7 @@ def test_nccl_bands_equal_unsharded(world):
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, w, h, q)) for r in range(world)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, w, h, q, p2p)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get() for _ in range(world)]

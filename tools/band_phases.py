@@ -11,6 +11,8 @@ W = H = 16384
 y0, rows = bands.band_rows(H, world, rank)
 be = bands.CudaBandBackend(W, rows, y0, H, device=local)
 be.load(synth.giga_rows(y0, y0 + rows, W, H))
+if world > 1 and os.environ.get("B2C_BAND_NCCL", "0") != "1":
+    be.enable_p2p(dist, rank, world)
 bc = bands.BandCanny(be, rank, world, dist if world > 1 else None)
 for _ in range(3):
     bc.run()
@@ -25,7 +27,9 @@ for rep in range(2):
     be.stencil(); t.append(T()); names.append("stencil")
     be.hysteresis(True, write_edges=False); t.append(T()); names.append("hyst0")
     r = 1
-    while world > 1:
+    if world > 1 and getattr(be, "p2p", False):
+        r = be.converge(); t.append(T()); names.append("p2p_rounds")
+    while world > 1 and not getattr(be, "p2p", False):
         bc._exchange(be.boundary(0), be.ghost(0), be.boundary(1), be.ghost(1)); t.append(T()); names.append("xchg")
         be.hysteresis(False, write_edges=False); t.append(T()); names.append("reentry")
         flag = be.seeded().clone(); dist.all_reduce(flag, op=dist.ReduceOp.MAX); v = int(flag.item()); t.append(T()); names.append("allreduce")

@@ -7,7 +7,7 @@ run() { # $1 = gpus, rest = bench args
   g=$1; shift
   if [ "$g" = 1 ]; then python bench.py --gpus 1 "$@"; else python -m torch.distributed.run --nnodes=1 --nproc-per-node $g --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $g "$@"; fi
 }
-for g in 1 2 4 8; do
+for g in ${GS:-1 2 4 8}; do
   [ $g -le $N ] || continue
   for wl in $WLS; do
     case $wl in
