@@ -175,7 +175,9 @@ class BandCanny:
         b.ghost(1).zero_()
         self.exchange_input_halos()
         b.stencil()
-        b.hysteresis(True, write_edges=False)   # band-local fixpoint (planes + union-find forest are kept)
+        # band-local fixpoint (planes + union-find forest are kept).  Every resolve pass also writes the u8 edge map,
+        # so there is no separate expansion pass once the rounds have converged.
+        b.hysteresis(True, write_edges=True)
         rounds = 1
         if self.world > 1 and getattr(b, "p2p", False):
             rounds = max(1, b.converge() - 1)   # device-side rounds over NVLink peer memory (the last one finds nothing new)
@@ -185,13 +187,12 @@ class BandCanny:
             # (One all_gather of rows + flag per round instead of send/recv + all_reduce was measured SLOWER: the
             # extra small tensor ops on the host cost more than the second NCCL launch.)
             self._exchange(b.boundary(0), b.ghost(0), b.boundary(1), b.ghost(1))
-            b.hysteresis(False, write_edges=False)
+            b.hysteresis(False, write_edges=True)
             flag = b.seeded().clone()
             d.all_reduce(flag, op=d.ReduceOp.MAX, group=self.group)
             if int(flag.item()) == 0:
                 break
             rounds += 1
-        b.hysteresis(False, write_edges="only")   # the bit plane is final: expand it to the u8 edge map
         self.rounds = rounds
         return rounds
 
@@ -214,7 +215,7 @@ def run_local(backends):
     for b in backends:
         b.stencil()
     for b in backends:
-        b.hysteresis(True, write_edges=False)
+        b.hysteresis(True, write_edges=True)
     rounds = 1
     while n > 1:
         for b in backends:
@@ -226,12 +227,10 @@ def run_local(backends):
         for b in backends:
             b.sync()
         for b in backends:
-            b.hysteresis(False, write_edges=False)
+            b.hysteresis(False, write_edges=True)
         if not any(bool(b.seeded().item()) for b in backends):
             break
         rounds += 1
-    for b in backends:
-        b.hysteresis(False, write_edges="only")
     for b in backends:
         b.sync()
     return rounds

@@ -1036,6 +1036,9 @@ int b2c_band_p2p_converge(b2c_handle c, int rounds_per_sync, int *rounds_out, vo
   p.flags = c->d_flags;
   p.parent = c->d_parent;
   p.parent_frame_stride = (long long)c->rows_alloc * c->plane_pitch * 32;
+  p.edges = c->d_edges;   // every resolve also (re)writes the u8 edge map: no separate expansion pass after convergence
+  p.edges_pitch = (long long)c->edges_pitch;
+  p.edges_frame_stride = (long long)c->edges_frame_stride;
   p.skip = c->d_p2pctl + b2c::BP_DONE;
   p.need = c->d_p2pctl + b2c::BP_SEEDED;   // set by this round's seed kernel iff something new was seeded in this band
   b2c::B2cBandP2P q;
@@ -1052,7 +1055,7 @@ int b2c_band_p2p_converge(b2c_handle c, int rounds_per_sync, int *rounds_out, vo
     for (int k = 0; k < rounds_per_sync; ++k) {
       b2c::k_band_push<<<1, 256, 0, st>>>(p, q);
       b2c::k_band_seed<<<dim3((c->wpr + T - 1) / T, 2), T, 0, st>>>(p, q);
-      b2c::k_uf_resolve<false><<<gr, br, 0, st>>>(p, c->d_bcount);
+      b2c::k_uf_resolve<true><<<gr, br, 0, st>>>(p, c->d_bcount);
       c->launches += 3;
     }
     CK(c, cudaGetLastError());

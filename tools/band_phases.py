@@ -25,17 +25,17 @@ for rep in range(2):
     be.ghost(0).zero_(); be.ghost(1).zero_()
     bc.exchange_input_halos(); t.append(T()); names.append("halo")
     be.stencil(); t.append(T()); names.append("stencil")
-    be.hysteresis(True, write_edges=False); t.append(T()); names.append("hyst0")
+    be.hysteresis(True, write_edges=True); t.append(T()); names.append("hyst0")
     r = 1
     if world > 1 and getattr(be, "p2p", False):
         r = be.converge(); t.append(T()); names.append("p2p_rounds")
     while world > 1 and not getattr(be, "p2p", False):
         bc._exchange(be.boundary(0), be.ghost(0), be.boundary(1), be.ghost(1)); t.append(T()); names.append("xchg")
-        be.hysteresis(False, write_edges=False); t.append(T()); names.append("reentry")
+        be.hysteresis(False, write_edges=True); t.append(T()); names.append("reentry")
         flag = be.seeded().clone(); dist.all_reduce(flag, op=dist.ReduceOp.MAX); v = int(flag.item()); t.append(T()); names.append("allreduce")
         if v == 0: break
         r += 1
-    be.hysteresis(False, write_edges="only"); t.append(T()); names.append("expand")
+    t.append(T()); names.append("-")
     if rank == 0:
         print("rep", rep, "rounds", r, " ".join(f"{n}={1e6*(b-a):.0f}us" for n, a, b in zip(names, t, t[1:])), "total=%.0fus" % (1e6 * (t[-1] - t[0])))
 be.close()
