@@ -99,7 +99,7 @@ class CudaBandBackend:
     def halo_p2p(self):
         _lib.check(_lib.lib.b2c_band_p2p_halo(self._h, self._stream()), self._h, "b2c_band_p2p_halo")
 
-    def converge(self, rounds_per_sync=4):
+    def converge(self, rounds_per_sync=16):
         n = C.c_int(0)
         _lib.check(_lib.lib.b2c_band_p2p_converge(self._h, rounds_per_sync, C.byref(n), self._stream()), self._h, "b2c_band_p2p_converge")
         return n.value

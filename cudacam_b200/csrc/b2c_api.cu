@@ -939,8 +939,8 @@ int b2c_band_p2p_export(b2c_handle c, void *blob_144)
     const size_t bytes = b2c::bp_mailbox_words(c->wpr) * sizeof(uint32_t);
     CK(c, cudaMalloc(&c->d_mailbox, bytes));
     CK(c, cudaMemset(c->d_mailbox, 0, bytes));
-    CK(c, cudaMalloc(&c->d_p2pctl, 8 * sizeof(int)));
-    CK(c, cudaMemset(c->d_p2pctl, 0, 8 * sizeof(int)));
+    CK(c, cudaMalloc(&c->d_p2pctl, 64 * sizeof(int)));
+    CK(c, cudaMemset(c->d_p2pctl, 0, 64 * sizeof(int)));
     CK(c, cudaMallocHost(&c->h_p2pctl, 8 * sizeof(int)));
   }
   void *in;
@@ -1048,17 +1048,16 @@ int b2c_band_p2p_converge(b2c_handle c, int rounds_per_sync, int *rounds_out, vo
   CK(c, cudaMemsetAsync(c->d_p2pctl + b2c::BP_RUN_ROUNDS, 0, sizeof(int), st));
   CK(c, cudaMemsetAsync(c->d_p2pctl + b2c::BP_SEEDED, 0, sizeof(int), st));
   CK(c, cudaMemsetAsync(c->d_p2pctl + b2c::BP_SEEDED, 1, 1, st));
-  const int T = b2c::UFK_THREADS;
-  const int tx = c->wpr >= 256 ? 256 : c->wpr > 32 ? 64 : 32, ty = 256 / tx;
-  const dim3 gr((c->wpr + tx - 1) / tx, (c->rows_alloc + ty - 1) / ty, 1), br(tx, ty);
-  for (int total = 0; total < 4096; total += rounds_per_sync) {
-    for (int k = 0; k < rounds_per_sync; ++k) {
-      b2c::k_band_push<<<1, 256, 0, st>>>(p, q);
-      b2c::k_band_seed<<<dim3((c->wpr + T - 1) / T, 2), T, 0, st>>>(p, q);
-      b2c::k_uf_resolve<true><<<gr, br, 0, st>>>(p, c->d_bcount);
-      c->launches += 3;
-    }
-    CK(c, cudaGetLastError());
+  int per_sm = 0;
+  CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b2c::k_band_rounds<true>, 256, 0));
+  if (per_sm < 1) return B2C_ERR_CUDA;
+  const long long nwords = (long long)c->rows_alloc * c->wpr;
+  const int grid = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * std::min(per_sm, 4), (nwords + 255) / 256));
+  int max_rounds = std::max(rounds_per_sync, 1);
+  void *args[] = { &p, &q, &max_rounds };
+  for (int total = 0; total < 4096; total += max_rounds) {
+    CK(c, cudaLaunchCooperativeKernel((const void *)b2c::k_band_rounds<true>, dim3(grid), dim3(256), args, 0, st));
+    c->launches += 1;
     CK(c, cudaMemcpyAsync(c->h_p2pctl, c->d_p2pctl, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
     if (c->h_p2pctl[b2c::BP_ERROR]) {
@@ -1164,6 +1163,13 @@ int b2c_get_info(b2c_handle c, const char *name)
     if (cudaMemcpy(v, c->d_flags, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return B2C_ERR_CUDA;
     const int k = name[5] - '0';
     return (k >= 0 && k < 8) ? v[8 + k] : B2C_ERR_INVALID;
+  }
+  if (!strncmp(name, "p2p_stamp", 9)) {   // time stamps of the last k_band_rounds launch (ns, low 32 bits); "p2p_stamp55" = how many
+    const int k = atoi(name + 9);
+    int v = 0;
+    if (!c->d_p2pctl || k < 0 || k > 55) return B2C_ERR_INVALID;
+    if (cudaMemcpy(&v, c->d_p2pctl + 8 + k, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return B2C_ERR_CUDA;
+    return v;
   }
   if (!strncmp(name, "hyst_phase_us", 13)) {   // phase times of the last union-find hysteresis run with "hyst_phase_timing" on (us)
     const int k = name[13] - '0';

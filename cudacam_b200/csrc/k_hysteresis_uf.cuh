@@ -530,57 +530,70 @@ __global__ void __launch_bounds__(UFK_THREADS) k_uf_seed(const B2cHystParams p)
 }
 
 // a run survives iff its root is node 0; then (EXPAND) the final S word goes out as 32 bytes of the u8 {0,255} edge map.
-// One thread per plane word.
+// Body for one plane word; returns true if the word gained edge bits.
+// (s, c = the word's S and C values, already loaded: lets a caller keep many loads in flight)
+template <bool EXPAND, bool ONLY_CHANGED = false>
+__device__ __forceinline__ bool uf_resolve_expand_word_sc(const B2cHystParams &p, int f, int y, int xw, int W32, uint32_t s, const uint32_t c)
+{
+  bool changed = false;
+  const long long o = f * p.plane_frame_stride + (long long)y * p.plane_pitch + xw;
+  uint32_t m = c & ~s;
+  if (m) {
+    int *P = p.parent + f * p.parent_frame_stride;
+    const int base = y * W32 + xw * 32 + 1;
+    uint32_t add = 0u;
+    while (m) {
+      const uint32_t lo = m & (0u - m);
+      const uint32_t run = m & ~(m + lo);
+      m &= ~run;
+      if (uf_find_final(P, base + __ffs((int)lo) - 1) == 0) add |= run;
+    }
+    if (add) {
+      s |= add;
+      p.S[o] = s;
+      changed = true;
+    }
+  }
+  if (EXPAND && (!ONLY_CHANGED || changed)) {   // (ONLY_CHANGED: the map already holds the previous state of every word)
+    uint8_t *out = p.edges + f * p.edges_frame_stride + (long long)y * p.edges_pitch + xw * 32;
+    const int n = min(32, p.w - xw * 32);
+    if (n == 32 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const uint32_t bits = (s >> (16 * hh)) & 0xFFFFu;
+        uint4 v;
+        v.x = (((bits & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+        v.y = ((((bits >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+        v.z = ((((bits >> 8) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+        v.w = ((((bits >> 12) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+        reinterpret_cast<uint4 *>(out)[hh] = v;
+      }
+    } else {
+      for (int k = 0; k < n; ++k) out[k] = ((s >> k) & 1u) ? 255 : 0;
+    }
+  }
+  return changed;
+}
+template <bool EXPAND, bool ONLY_CHANGED = false>
+__device__ __forceinline__ bool uf_resolve_expand_word(const B2cHystParams &p, int f, int y, int xw, int W32)
+{
+  const long long o = f * p.plane_frame_stride + (long long)y * p.plane_pitch + xw;
+  return uf_resolve_expand_word_sc<EXPAND, ONLY_CHANGED>(p, f, y, xw, W32, p.S[o], p.C[o]);
+}
+
+// One thread per plane word: block = (blockDim.x words) x (blockDim.y rows); grid: x = word blocks of a row, y = row
+// blocks, z = frame.
 template <bool EXPAND>
 __global__ void __launch_bounds__(UFK_THREADS) k_uf_resolve(const B2cHystParams p, int *bcount)
 {
   if ((p.skip && __ldcg(p.skip)) || (p.need && __ldcg(p.need) == 0)) return;
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) bcount[blockIdx.z] = 0;   // the border list of this frame is consumed
-  // block = (blockDim.x words) x (blockDim.y rows); grid: x = word blocks of a row, y = row blocks, z = frame
   const int wpr = (p.w + 31) >> 5, W32 = p.plane_pitch * 32;
-  bool changed = false;
   const int xw = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, f = blockIdx.z;
-  if (xw < wpr && y < p.h) {
-    const long long o = f * p.plane_frame_stride + (long long)y * p.plane_pitch + xw;
-    uint32_t s = p.S[o];
-    uint32_t m = p.C[o] & ~s;
-    if (m) {
-      int *P = p.parent + f * p.parent_frame_stride;
-      const int base = y * W32 + xw * 32 + 1;
-      uint32_t add = 0u;
-      while (m) {
-        const uint32_t lo = m & (0u - m);
-        const uint32_t run = m & ~(m + lo);
-        m &= ~run;
-        if (uf_find_final(P, base + __ffs((int)lo) - 1) == 0) add |= run;
-      }
-      if (add) {
-        s |= add;
-        p.S[o] = s;
-        changed = true;
-      }
-    }
-    if (EXPAND) {
-      uint8_t *out = p.edges + f * p.edges_frame_stride + (long long)y * p.edges_pitch + xw * 32;
-      const int n = min(32, p.w - xw * 32);
-      if (n == 32 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const uint32_t bits = (s >> (16 * hh)) & 0xFFFFu;
-          uint4 v;
-          v.x = (((bits & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
-          v.y = ((((bits >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
-          v.z = ((((bits >> 8) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
-          v.w = ((((bits >> 12) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
-          reinterpret_cast<uint4 *>(out)[hh] = v;
-        }
-      } else {
-        for (int k = 0; k < n; ++k) out[k] = ((s >> k) & 1u) ? 255 : 0;
-      }
-    }
-  }
-  // one plain store per warp at most, and only while the flag is still clear (a same-address atomic per thread
-  // serialises in L2 and cost more than the whole phase)
+  bool changed = false;
+  if (xw < wpr && y < p.h) changed = uf_resolve_expand_word<EXPAND>(p, f, y, xw, W32);
+  // a plain store, and only while the flag is still clear (a same-address atomic per thread serialises in L2 and cost
+  // more than the whole phase)
   if (changed && __ldcg(p.flags + 4) == 0) __stcg(p.flags + 4, 1);
 }
 

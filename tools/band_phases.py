@@ -2,7 +2,7 @@
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
-from cudacam_b200 import bands, synth
+from cudacam_b200 import bands, synth, _lib
 world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 if world > 1:
@@ -36,6 +36,10 @@ for rep in range(2):
         if v == 0: break
         r += 1
     t.append(T()); names.append("-")
+    if getattr(be, "p2p", False):
+        n = _lib.lib.b2c_get_info(be._h, b"p2p_stamp55")
+        st = [_lib.lib.b2c_get_info(be._h, b"p2p_stamp%d" % k) & 0xFFFFFFFF for k in range(n)]
+        print("rank", rank, "rounds kernel stamps (us since start):", " ".join("%.1f" % (((x - st[0]) & 0xFFFFFFFF) / 1000.0) for x in st), flush=True)
     if rank == 0:
         print("rep", rep, "rounds", r, " ".join(f"{n}={1e6*(b-a):.0f}us" for n, a, b in zip(names, t, t[1:])), "total=%.0fus" % (1e6 * (t[-1] - t[0])))
 be.close()
