@@ -372,6 +372,7 @@ def run_giga(args, wl):
     sampler = ClockSampler(local)
     sampler.start()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = be.launches
     a.record()
     rounds = 0
     for _ in range(args.steps):
@@ -379,6 +380,7 @@ def run_giga(args, wl):
     b.record()
     barrier()
     clocks = sampler.stop()
+    launches = be.launches - l0
     t = torch.tensor([a.elapsed_time(b)], device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -409,7 +411,7 @@ def run_giga(args, wl):
                          "frac": px * 4.0 / (total_ms / args.steps * 1e-3) / 1e9 / world / peak, "traffic": None, "peak_source": which},
             "e2e": {"value": px * e2e_steps / float(t.item()) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": px * 3, "d2h_bytes_per_step": px, "steps": e2e_steps,
                     "api": "CudaBandBackend.load (pageable host band) + BandCanny.run + edges() download"},
-            "gpu_launches": None, "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))
     be.close()

@@ -132,6 +132,11 @@ class CudaBandBackend:
     def sync(self):
         self.torch.cuda.synchronize(self.device)
 
+    @property
+    def launches(self):
+        """Kernels launched by this band's handle so far."""
+        return _lib.lib.b2c_launch_count(self._h)
+
     def edges(self):
         out = np.empty((self.rows, self.width), np.uint8)
         self.torch.cuda.synchronize(self.device)

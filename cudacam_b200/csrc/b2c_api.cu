@@ -49,6 +49,7 @@ struct b2c_ctx {
   int march_stagger_ns = 4000;
   int hyst_impl = 0;          // 0 union-find as 4 launches, 1 tile rounds (cooperative), 2 union-find as one cooperative launch
   int hyst_tile_rows = 16;
+  int uf_spread = 1;
   int hyst_max_rounds = 1 << 20;
 
   // geometry
@@ -318,6 +319,7 @@ int launch_hysteresis(b2c_ctx *c, int n, uint8_t *edges, size_t edges_pitch, siz
   p.skip_expand = skip_expand;
   p.parent = c->d_parent;
   p.parent_frame_stride = (long long)c->rows_alloc * c->plane_pitch * 32;
+  p.spread = c->uf_spread;
   void *args[] = { &p };
   if (c->hyst_impl == 0 && c->wpr <= 1024) {   // (list entries hold the word index in 10 bits: wider images take the cooperative kernel)
     // union-find as three ordinary launches (tile, border, resolve+expand; row-band re-entry: seed, resolve) -- no
@@ -1129,6 +1131,10 @@ int b2c_set_option(b2c_handle c, const char *name, int value)
   if (!strcmp(name, "march_stagger_ns")) {
     if (value < 0) return B2C_ERR_INVALID;
     c->march_stagger_ns = value;
+    return B2C_OK;
+  }
+  if (!strcmp(name, "uf_spread")) {
+    c->uf_spread = value != 0;
     return B2C_OK;
   }
   if (!strcmp(name, "hyst_phase_timing")) {

@@ -73,6 +73,7 @@ struct B2cHystParams {
   int tile_rows;
   int skip_init;             // 1 = S/C planes already built (row-band mode re-entry)
   int skip_expand;           // 1 = do not write edges (row-band mode intermediate rounds)
+  int spread;                // tile kernel: 1 = deal the compacted work items round-robin to the warps, 0 = pack them
   const int *skip;           // if non-null and *skip != 0 the resolve kernel does nothing (row-band P2P rounds after convergence)
   const int *need;           // if non-null and *need == 0 the resolve kernel does nothing (this band was not seeded in this round)
   int *parent;               // union-find parents, one int per pixel of the padded plane (only weak pixels are used)

@@ -382,8 +382,12 @@ __global__ void __launch_bounds__(UT_THREADS) k_uf_tile(const B2cHystParams p, u
   const int nitems = WC[UT_THREADS / 32];
   // ---- the remaining phases run on the compacted list: thread k takes the k-th word that holds weak pixels, so the
   // divergent per-run loops fill whole warps instead of a few lanes of every warp
-  const bool act = tid < nitems;
-  const int t = act ? IT[tid] : 0, ly = t >> 3, lw = t & 7, y = y0 + ly, xw = xw0 + lw;
+  // Items are dealt round-robin to the 8 warps (item = lane * 8 + warp), not packed into warp 0: the per-run loops
+  // are dependent chains of shared-memory atomics, so eight warps with a few busy lanes each finish sooner than one
+  // full warp while the other seven wait at the barrier (p.spread == 0 keeps the packed order for comparison).
+  const int item = p.spread ? lane * (UT_THREADS / 32) + warp : tid;
+  const bool act = item < nitems;
+  const int t = act ? IT[item] : 0, ly = t >> 3, lw = t & 7, y = y0 + ly, xw = xw0 + lw;
   const uint32_t wd = act ? LW[t] : 0u;
   const int lbase = 1 + t * 16;   // local node of the first run of this word
   if (act) {

@@ -79,7 +79,7 @@ __attribute__((visibility("default"))) int emu_hysteresis(const uint32_t *map2, 
   p.S = S.data() + pitch; p.C = Cc.data() + pitch; p.plane_pitch = pitch; p.plane_frame_stride = fs;
   p.w = w; p.h = h; p.nframes = nframes;
   p.edges = edges; p.edges_pitch = w; p.edges_frame_stride = (long long)w * h;
-  p.flags = flags; p.max_rounds = 1 << 20; p.tile_rows = tile_rows;
+  p.flags = flags; p.max_rounds = 1 << 20; p.tile_rows = tile_rows; p.spread = 1;
   std::vector<int> parent((size_t)nframes * h * pitch * 32, -12345);
   p.parent = parent.data(); p.parent_frame_stride = (long long)h * pitch * 32;
   if (tile_rows > 0)

@@ -134,3 +134,45 @@ def test_hysteresis_unionfind4_ghost_rows_and_reentry():
     gb = np.zeros((w + 31) // 32, np.uint32); gb[1] = 1 << (50 - 32)
     edges, bits, _, changed = E.hysteresis(O.thresh_to_map2(t), w, grid_blocks=2, tile_rows=-1, ghost_top=gt, ghost_bot=gb)
     assert edges[0][:, 10].all() and edges[0][5:, 50].all() and not edges[0][:, 80].any() and not edges[0][:5, 50].any()
+
+
+@pytest.mark.parametrize("dens,seed", [(0.08, 1), (0.25, 2), (0.6, 3)])
+def test_hysteresis_unionfind4_many_tiles(dens, seed):
+    """Random weak maps spanning several 32-row x 256-pixel tiles in both directions, sparse strong seeds: exercises the
+    tile-local forests, the border lists (top rows, left / right word columns, NW / NE across tile corners) and resolve."""
+    rng = np.random.default_rng(seed)
+    w, h = 600, 75
+    t = np.where(rng.random((h, w)) < dens, 128, 0).astype(np.uint8)
+    t[rng.random(t.shape) < 0.0015] = 255
+    # long chains along and across the tile borders
+    t[31:33, 100:500] = np.where(t[31:33, 100:500] == 255, 255, 128)
+    t[5:70, 255:257] = np.where(t[5:70, 255:257] == 255, 255, 128)
+    edges, bits, _, _ = E.hysteresis(O.thresh_to_map2(t), w, grid_blocks=2, tile_rows=-1)
+    want = O.hysteresis(t)
+    assert np.array_equal(edges[0], want)
+    assert np.array_equal(bits[0], O.edges_to_bits(want))
+
+
+def test_hysteresis_unionfind4_diagonal_staircase_across_tiles():
+    """A one-pixel diagonal staircase crosses tile corners (NW / NE unions across both a row and a word boundary)."""
+    w, h = 520, 70
+    t = np.zeros((h, w), np.uint8)
+    for i in range(60):
+        t[5 + i, 225 + i] = 128          # down-right through (32, 256)
+        t[5 + i, 290 - i] = 128          # down-left through (32 + ..., 256)
+    t[5, 225] = 255
+    t[64, 231] = 255
+    edges, _, _, _ = E.hysteresis(O.thresh_to_map2(t), w, grid_blocks=2, tile_rows=-1)
+    assert np.array_equal(edges[0], O.hysteresis(t))
+
+
+@pytest.mark.parametrize("w,h,rb", [(8, 3, 16), (240, 36, 36), (248, 37, 26), (480, 12, 6), (1000, 23, 16)])
+def test_march_geometry_corner_cases(w, h, rb):
+    """Strip / band boundaries of the marching kernel: widths around multiples of 240, heights around the block size."""
+    f = synth.frame("scene", 40 + w, w, h)
+    r = O.canny(f, 10, 40, want_edges=False)
+    stride = (w * 3 + 15) // 16 * 16
+    buf = np.zeros((h + 8, stride), np.uint8)
+    buf[4:4 + h, :w * 3] = f.reshape(h, w * 3)
+    e = E.stencil_raw(buf, 4, w, h, 10, 40, impl=100 + rb)
+    assert e is not None and np.array_equal(e, O.thresh_to_map2(r["thresh"]))

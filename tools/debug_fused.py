@@ -1,4 +1,5 @@
-"""Debug helper: fused vs tile stencil kernel on the GPU, prints where the 2-bit maps differ."""
+"""Debug helper: the three stencil kernels (0 marching, 1 tile, 2 fused CTA-tile) on the GPU against the oracle; prints
+where the 2-bit maps differ."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
@@ -23,8 +24,11 @@ for kind, w, h, seed in [("scene", 240, 60, 1), ("scene", 1280, 720, 0xC0FFEE), 
         c.set_option("stencil_impl", 1)
         c.run(f)
         tile = dec(c.map2(), w)
+        c.set_option("stencil_impl", 2)
+        c.run(f)
+        fused = dec(c.map2(), w)
     d = np.argwhere(got != want)
-    print(kind, w, h, "tile ok", np.array_equal(tile, want), "fused diffs", len(d))
+    print(kind, w, h, "tile ok", np.array_equal(tile, want), "fused ok", np.array_equal(fused, want), "march diffs", len(d))
     if len(d):
         print("  rows", d[:, 0].min(), d[:, 0].max(), "cols", d[:, 1].min(), d[:, 1].max())
         print("  got/want histogram:", {(int(a), int(b)): int(((got == a) & (want == b)).sum()) for a in (0, 128, 255) for b in (0, 128, 255) if a != b})

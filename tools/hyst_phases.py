@@ -11,12 +11,14 @@ for (w, h, n) in [(3840, 2160, 1), (1920, 1080, 64), (1920, 1080, 32), (1920, 10
     d_in = torch.from_numpy(host.reshape(-1)).cuda()
     c = cb.CannyEdge(w, h, max_batch=max(n, 2))
     c.set_option("hyst_phase_timing", 1)
-    acc = np.zeros(3)
-    for it in range(8):
-        _lib.check(lib.b2c_run_device(c._h, d_in.data_ptr(), w * 3, w * 3 * h, n, None, 0, 0, None))
-        c.sync()
-        if it >= 3:
-            acc += [c.info("hyst_phase_us%d" % k) for k in range(3)]
-    acc /= 5
-    print(w, h, n, "phase us: tile %.1f border %.1f resolve+expand %.1f  total %.1f" % (*acc, acc.sum()))
+    for spread in (1, 0):
+        c.set_option("uf_spread", spread)
+        acc = np.zeros(3)
+        for it in range(8):
+            _lib.check(lib.b2c_run_device(c._h, d_in.data_ptr(), w * 3, w * 3 * h, n, None, 0, 0, None))
+            c.sync()
+            if it >= 3:
+                acc += [c.info("hyst_phase_us%d" % k) for k in range(3)]
+        acc /= 5
+        print(w, h, n, "spread", spread, "phase us: tile %.1f border %.1f resolve+expand %.1f  total %.1f" % (*acc, acc.sum()))
     c.close()
