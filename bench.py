@@ -179,7 +179,9 @@ def run_reference(args, wl):
                    "hysteresis_launches_mean": float(np.mean(iters)) + 1},
         "cpu_baseline": {"value": mpx, "unit": "Mpixel/s", "cores": 1, "kind": "reference",
                          "sample": f"{args.steps} x {n} frames of {w}x{h} through oracle/_ref (the reference's CUDA kernels on this GPU, 1 host thread; it has no CPU path)"},
-        "e2e": {"value": mpx, "unit": "Mpixel/s", "h2d_bytes_per_step": n * w * h * 3, "d2h_bytes_per_step": 0},
+        # contract of the reference arm: its e2e repeats the line's own value with zero transfer bytes (the upload of
+        # every frame from pageable host memory is inside the reference's run() and therefore inside `value`)
+        "e2e": {"value": mpx, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "clocks": clocks,
     }
     print(json.dumps(line))
@@ -337,8 +339,9 @@ def run_ours(args, wl):
 
 def run_giga(args, wl):
     """BASELINE configs[4]: one 16384x16384 image, one row band per rank (strong scaling).  A step = 4-row input halo
-    exchange with the neighbour ranks (NCCL send/recv), fused stencil on the band, then band-local hysteresis +
-    boundary-row exchange + convergence all-reduce until the global fixpoint, and the u8 expansion."""
+    exchange with the neighbour ranks (peer stores over NVLink, or NCCL send/recv), fused stencil on the band, then band-local hysteresis +
+    boundary-row exchange + convergence flags (device side) or all-reduce (NCCL) until the global fixpoint; every
+    resolve pass keeps the u8 edge map current."""
     import torch
     import torch.distributed as dist
     from cudacam_b200 import bands, synth

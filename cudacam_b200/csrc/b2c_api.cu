@@ -4,7 +4,8 @@
 //   ctor/_initAlloc (:16-38,:340-385)  -> b2c_create          (device buffers, pinned staging, streams)
 //   run            (:49-120)           -> b2c_run             (one host frame, blocking, stage select)
 //   _loadInputImage(:122-152)          -> async pitched H2D copy on the handle's stream
-//   _run* x6 + CPU hysteresis loop (:214-338) -> 1 fused stencil launch + 1 cooperative hysteresis launch
+//   _run* x6 + CPU hysteresis loop (:214-338) -> 1 fused stencil launch (k_stencil_march) + 3 union-find launches
+//                                                 (k_uf_tile, k_uf_border, k_uf_resolve), no host round trip
 //   _sendOutputToOpenGL (:154-212)     -> the VIEW buffer (tight w*h bytes, what the PBO receives)
 //   _start/_endCudaTimer (:409-430)    -> event pairs read back only by b2c_last_timings
 //   checkCudaErrors -> exit (helper.hpp:4-17) -> status codes, never exit
@@ -47,7 +48,7 @@ struct b2c_ctx {
   int stencil_impl = 0;       // 0 marching warp-per-strip kernel, 1 staged tile kernel, 2 fused CTA-tile kernel
   int march_rb = 0;           // rows per band of the marching kernel, 0 = automatic
   int march_stagger_ns = 4000;
-  int hyst_impl = 0;          // 0 union-find as 4 launches, 1 tile rounds (cooperative), 2 union-find as one cooperative launch
+  int hyst_impl = 0;          // 0 union-find as 3 launches (tile, border, resolve), 1 tile rounds (cooperative), 2 union-find as one cooperative launch
   int hyst_tile_rows = 16;
   int uf_spread = 1;
   int hyst_max_rounds = 1 << 20;
@@ -195,7 +196,7 @@ int alloc_common(b2c_ctx *c)
   }
   for (auto &e : c->ev_t) CK(c, cudaEventCreate(&e));
 
-  // hysteresis launch geometry: persistent cooperative grid, as many CTAs as fit
+  // launch geometry of the two cooperative hysteresis variants (options hyst_impl 1 / 2): as many CTAs as fit
   c->hyst_smem = b2c::hyst_smem_bytes(c->hyst_tile_rows);
   CK(c, cudaFuncSetAttribute(b2c::k_hysteresis, cudaFuncAttributeMaxDynamicSharedMemorySize, c->hyst_smem));
   int per_sm = 0;
