@@ -337,14 +337,14 @@ int launch_hysteresis(b2c_ctx *c, int n, uint8_t *edges, size_t edges_pitch, siz
     if (pt) cudaEventRecord(c->ev_h[1], st);
     {
       // border list: typically ~12 % of bcap entries; a quarter of the worst case in blocks, grid-stride for the rest
-      const int gb = std::max(1, (c->bcap / 4 + T - 1) / T);
+      const int gb = std::max(1, (c->bcap + T - 1) / T);   // 4 threads per entry, a quarter of the worst case in blocks
       if (!skip_init) {
         b2c::k_uf_border<<<dim3(gb, 1, n), T, 0, st>>>(p, c->d_blist, c->d_bcount, c->bcap);
         c->launches++;
       }
       if (pt) cudaEventRecord(c->ev_h[2], st);
       const int tx = c->wpr >= 256 ? 256 : c->wpr > 32 ? 64 : 32, ty = 256 / tx;   // 256 threads = tx words x ty rows
-      const dim3 gr((c->wpr + tx - 1) / tx, (c->rows_alloc + ty - 1) / ty, n), br(tx, ty);
+      const dim3 gr((c->wpr + tx - 1) / tx, (c->rows_alloc + 2 * ty - 1) / (2 * ty), n), br(tx, ty);   // a thread takes 2 rows
       if (edges && !skip_expand) b2c::k_uf_resolve<true><<<gr, br, 0, st>>>(p, c->d_bcount);
       else b2c::k_uf_resolve<false><<<gr, br, 0, st>>>(p, c->d_bcount);
       if (pt) cudaEventRecord(c->ev_h[3], st);

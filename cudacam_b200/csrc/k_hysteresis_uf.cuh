@@ -489,12 +489,16 @@ __global__ void __launch_bounds__(UT_THREADS) k_uf_tile(const B2cHystParams p, u
 // Grid: x = blocks over a frame's list, z = frame.
 __global__ void __launch_bounds__(UFK_THREADS) k_uf_border(const B2cHystParams p, const uint32_t *blist, const int *bcount, const int bcap)
 {
-  const int f = blockIdx.z, n = bcount[f], W32 = p.plane_pitch * 32;
+  // Four threads per list entry, one per kind of neighbour (W, N, NW, NE): a union is a chain of dependent L2 round
+  // trips (two finds + an atomicMin), and a word's unions done one after the other by ONE thread were the whole
+  // duration of this kernel (22 us even for a single frame).
+  const int f = blockIdx.z, n = 4 * bcount[f], W32 = p.plane_pitch * 32;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t e = blist[(long long)f * bcap + i];
-    const int y = (int)(e >> 10), xw = (int)(e & 1023u);
+    const uint32_t e = blist[(long long)f * bcap + (i >> 2)];
+    const int kind = i & 3, y = (int)(e >> 10), xw = (int)(e & 1023u);
     const bool top = (y % UT_ROWS) == 0, left = (xw % UT_WORDS) == 0, right = (xw % UT_WORDS) == UT_WORDS - 1;
-    uf_union_word(p, f, y, xw, W32, left, top, top || left, top || right);
+    const bool doW = kind == 0 && left, doN = kind == 1 && top, doNW = kind == 2 && (top || left), doNE = kind == 3 && (top || right);
+    if (doW || doN || doNW || doNE) uf_union_word(p, f, y, xw, W32, doW, doN, doNW, doNE);
   }
 }
 
@@ -585,17 +589,23 @@ __device__ __forceinline__ bool uf_resolve_expand_word(const B2cHystParams &p, i
   return uf_resolve_expand_word_sc<EXPAND, ONLY_CHANGED>(p, f, y, xw, W32, p.S[o], p.C[o]);
 }
 
-// One thread per plane word: block = (blockDim.x words) x (blockDim.y rows); grid: x = word blocks of a row, y = row
-// blocks, z = frame.
+// One thread per plane word of TWO rows (both rows' loads in flight before either is looked at): block =
+// (blockDim.x words) x (2 * blockDim.y rows); grid: x = word blocks of a row, y = row blocks, z = frame.
 template <bool EXPAND>
 __global__ void __launch_bounds__(UFK_THREADS) k_uf_resolve(const B2cHystParams p, int *bcount)
 {
   if ((p.skip && __ldcg(p.skip)) || (p.need && __ldcg(p.need) == 0)) return;
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) bcount[blockIdx.z] = 0;   // the border list of this frame is consumed
   const int wpr = (p.w + 31) >> 5, W32 = p.plane_pitch * 32;
-  const int xw = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, f = blockIdx.z;
+  const int xw = blockIdx.x * blockDim.x + threadIdx.x, y = 2 * (blockIdx.y * blockDim.y + threadIdx.y), f = blockIdx.z;
   bool changed = false;
-  if (xw < wpr && y < p.h) changed = uf_resolve_expand_word<EXPAND>(p, f, y, xw, W32);
+  if (xw < wpr && y < p.h) {
+    const long long o = f * p.plane_frame_stride + (long long)y * p.plane_pitch + xw;
+    const bool two = y + 1 < p.h;
+    const uint32_t s0 = p.S[o], c0 = p.C[o], s1 = two ? p.S[o + p.plane_pitch] : 0u, c1 = two ? p.C[o + p.plane_pitch] : 0u;
+    changed = uf_resolve_expand_word_sc<EXPAND>(p, f, y, xw, W32, s0, c0);
+    if (two) changed |= uf_resolve_expand_word_sc<EXPAND>(p, f, y + 1, xw, W32, s1, c1);
+  }
   // a plain store, and only while the flag is still clear (a same-address atomic per thread serialises in L2 and cost
   // more than the whole phase)
   if (changed && __ldcg(p.flags + 4) == 0) __stcg(p.flags + 4, 1);

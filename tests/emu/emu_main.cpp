@@ -114,7 +114,7 @@ __attribute__((visibility("default"))) int emu_hysteresis(const uint32_t *map2, 
         emu::launch(dim3((wpr + b2c::UFK_THREADS - 1) / b2c::UFK_THREADS, 2, nframes), dim3(b2c::UFK_THREADS), 0, false, [=] { b2c::k_uf_seed(p); });
       }
       const int tx = 32, ty = 4;
-      const dim3 gr((wpr + tx - 1) / tx, (h + ty - 1) / ty, nframes), br(tx, ty);
+      const dim3 gr((wpr + tx - 1) / tx, (h + 2 * ty - 1) / (2 * ty), nframes), br(tx, ty);   // a thread takes 2 rows
       if (rep + 1 < reps) emu::launch(gr, br, 0, false, [=] { b2c::k_uf_resolve<false>(p, bcp); });
       else emu::launch(gr, br, 0, false, [=] { b2c::k_uf_resolve<true>(p, bcp); });
     }
