@@ -89,10 +89,14 @@ class CannyEdge:
 
     # -- run (cannyEdgeH.cu:49-120) -----------------------------------------------------------------------------
     def run(self, frame, final_stage=CannyStage.HYSTER):
-        """frame: (h, w, 3) uint8 BGR host array (rows may be strided, like cv::Mat::step)."""
+        """frame: (h, w, channels) uint8 host array -- BGR8, BGRA8 or GRAY8 ((h, w) also accepted) as given to the
+        constructor; rows may be strided, like cv::Mat::step."""
         f = np.asarray(frame)
-        if f.dtype != np.uint8 or f.ndim != 3 or f.shape[2] != 3 or f.strides[2] != 1 or f.strides[1] != 3:
-            raise ValueError("frame must be an (h, w, 3) uint8 array with packed BGR pixels")
+        if f.ndim == 2:
+            f = f[:, :, None]
+        ch = self.channels
+        if f.dtype != np.uint8 or f.ndim != 3 or f.shape[2] != ch or f.strides[2] != 1 or f.strides[1] != ch:
+            raise ValueError(f"frame must be an (h, w, {ch}) uint8 array with packed pixels")
         if f.shape[0] != self.height or f.shape[1] != self.width:
             raise _lib.B2cError(_lib.ERR_SIZE, what="run")
         check(lib.b2c_run(self._h, f.ctypes.data, f.strides[0], int(final_stage)), self._h, "b2c_run")
@@ -101,14 +105,14 @@ class CannyEdge:
         check(lib.b2c_run_device(self._h, dev_ptr, row_stride, frame_stride, n, edges_ptr, edges_pitch, edges_frame_stride, stream), self._h, "b2c_run_device")
 
     def run_batch(self, frames, packed_bits=False, out=None):
-        """frames: (n, h, w, 3) uint8 host array -> (n, h, w) uint8 edge maps (or (n, h, ceil(w/32)) uint32 bit maps)."""
+        """frames: (n, h, w, channels) uint8 host array -> (n, h, w) uint8 edge maps (or (n, h, ceil(w/32)) uint32 bit maps)."""
         f = np.asarray(frames)
-        if f.dtype != np.uint8 or f.ndim != 4 or f.shape[1:] != (self.height, self.width, 3) or not f.flags.c_contiguous:
-            raise ValueError("frames must be a C-contiguous (n, h, w, 3) uint8 array")
+        if f.dtype != np.uint8 or f.ndim != 4 or f.shape[1:] != (self.height, self.width, self.channels) or not f.flags.c_contiguous:
+            raise ValueError("frames must be a C-contiguous (n, h, w, channels) uint8 array")
         n = f.shape[0]
         if out is None:
             out = np.empty((n, self.height, (self.width + 31) // 32), np.uint32) if packed_bits else np.empty((n, self.height, self.width), np.uint8)
-        check(lib.b2c_run_batch_host(self._h, f.ctypes.data, self.width * 3, n, out.ctypes.data, 1 if packed_bits else 0), self._h, "b2c_run_batch_host")
+        check(lib.b2c_run_batch_host(self._h, f.ctypes.data, self.width * self.channels, n, out.ctypes.data, 1 if packed_bits else 0), self._h, "b2c_run_batch_host")
         return out
 
     # -- accessors ----------------------------------------------------------------------------------------------
@@ -172,7 +176,9 @@ class CvPipeline:
         if self._edge is None or inputImage is None:
             return False
         f = np.asarray(inputImage)
-        if f.size == 0 or f.dtype != np.uint8 or f.ndim != 3 or f.shape[2] != 3:
+        if f.ndim == 2:
+            f = f[:, :, None]
+        if f.size == 0 or f.dtype != np.uint8 or f.ndim != 3 or f.shape[2] != self._edge.channels:
             return False
         self._edge.run(f, finalStage)
         return True

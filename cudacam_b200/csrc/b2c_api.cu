@@ -47,7 +47,7 @@ struct b2c_ctx {
   bool profiling = true;      // src/cvp/cannyEdgeH.cu:24
   int stencil_impl = 0;       // 0 marching warp-per-strip kernel, 1 staged tile kernel, 2 fused CTA-tile kernel
   int march_rb = 0;           // rows per band of the marching kernel, 0 = automatic
-  int march_stagger_ns = 4000;
+  int march_stagger_ns = 0;   // experiment knob, see k_stencil_march.cuh
   int hyst_impl = 0;          // 0 union-find as 3 launches (tile, border, resolve), 1 tile rounds (cooperative), 2 union-find as one cooperative launch
   int hyst_tile_rows = 16;
   int uf_spread = 1;
@@ -231,6 +231,7 @@ void fill_stencil_params(b2c_ctx *c, B2cStencilParams &p, const uint8_t *bgr, si
   p.y0 = c->band ? c->band_y0 : 0;
   p.h_glob = c->band ? c->h_glob : c->h;
   p.nframes = n;
+  p.channels = c->ch;
   p.map2 = c->d_map2;
   p.map_pitch = c->map_pitch;
   p.map_frame_stride = (long long)c->rows_alloc * c->map_pitch;
@@ -257,7 +258,7 @@ int launch_stencil(b2c_ctx *c, const uint8_t *bgr, size_t row_stride, size_t fra
   if (c->stencil_impl == 0 && b2c::march_supported(p)) {
     cudaError_t e = b2c::march_launch(p, c->sm_count, c->march_rb, st);
     if (e != cudaSuccess) return set_err(c, e, "k_stencil_march launch");
-  } else if (c->stencil_impl == 2 && b2c::fused_supported(p)) {
+  } else if (c->stencil_impl == 2 && c->ch == 3 && b2c::fused_supported(p)) {
     cudaError_t e = b2c::fused_launch(p, c->sm_count, st);
     if (e != cudaSuccess) return set_err(c, e, "k_stencil_fused launch");
   } else {
@@ -410,7 +411,7 @@ int b2c_create(b2c_handle *out, int device, int width, int height, int channels,
 {
   if (!out || width < 1 || height < 1 || max_batch < 1) return B2C_ERR_INVALID;
   *out = nullptr;
-  if (channels != 3) return B2C_ERR_UNSUPPORTED;
+  if (channels != 3 && channels != 1 && channels != 4) return B2C_ERR_UNSUPPORTED;   // BGR8, GRAY8, BGRA8
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
     (void)cudaGetLastError();
@@ -425,7 +426,7 @@ int b2c_create(b2c_handle *out, int device, int width, int height, int channels,
   c->max_batch = max_batch;
   c->rows_alloc = height;
   DevGuard g(device);
-  c->in_row_stride = round_up((size_t)width * 3, 16);
+  c->in_row_stride = round_up((size_t)width * channels, 16);
   c->in_frame_stride = c->in_row_stride * height;
   int rc = alloc_common(c);
   if (rc == B2C_OK && cudaMalloc(&c->d_in, (size_t)max_batch * c->in_frame_stride) != cudaSuccess) rc = set_err(c, cudaGetLastError(), "cudaMalloc(d_in)");
@@ -562,12 +563,12 @@ int b2c_run(b2c_handle c, const uint8_t *host_bgr, size_t row_stride, int final_
 {
   if (!c || !host_bgr || c->band) return B2C_ERR_INVALID;
   if (final_stage < B2C_STAGE_MONO || final_stage > B2C_STAGE_HYSTER) return B2C_ERR_INVALID;
-  if (row_stride < (size_t)c->w * 3) return B2C_ERR_SIZE;
+  if (row_stride < (size_t)c->w * c->ch) return B2C_ERR_SIZE;
   DevGuard g(c->dev);
   cudaStream_t st = c->s_main;
   const bool prof = c->profiling;
   if (prof) CK(c, cudaEventRecord(c->ev_t[0], st));
-  CK(c, cudaMemcpy2DAsync(c->d_in, c->in_row_stride, host_bgr, row_stride, (size_t)c->w * 3, c->h, cudaMemcpyHostToDevice, st));
+  CK(c, cudaMemcpy2DAsync(c->d_in, c->in_row_stride, host_bgr, row_stride, (size_t)c->w * c->ch, c->h, cudaMemcpyHostToDevice, st));
   if (prof) CK(c, cudaEventRecord(c->ev_t[1], st));
   c->last_in = c->d_in;
   c->last_row_stride = c->in_row_stride;
@@ -605,7 +606,7 @@ int b2c_run(b2c_handle c, const uint8_t *host_bgr, size_t row_stride, int final_
 int b2c_run_device(b2c_handle c, const uint8_t *dev_bgr, size_t row_stride, size_t frame_stride, int n, uint8_t *dev_edges, size_t edges_pitch, size_t edges_frame_stride, void *stream)
 {
   if (!c || !dev_bgr || c->band || n < 1 || n > c->max_batch) return B2C_ERR_INVALID;
-  if (row_stride < (size_t)c->w * 3) return B2C_ERR_SIZE;
+  if (row_stride < (size_t)c->w * c->ch) return B2C_ERR_SIZE;
   DevGuard g(c->dev);
   cudaStream_t st = stream ? (cudaStream_t)stream : c->s_main;
   if (!dev_edges) {
@@ -640,7 +641,7 @@ int b2c_run_device(b2c_handle c, const uint8_t *dev_bgr, size_t row_stride, size
 int b2c_stencil_device(b2c_handle c, const uint8_t *dev_bgr, size_t row_stride, size_t frame_stride, int n, void *stream)
 {
   if (!c || !dev_bgr || c->band || n < 1 || n > c->max_batch) return B2C_ERR_INVALID;
-  if (row_stride < (size_t)c->w * 3) return B2C_ERR_SIZE;
+  if (row_stride < (size_t)c->w * c->ch) return B2C_ERR_SIZE;
   DevGuard g(c->dev);
   return launch_stencil(c, dev_bgr, row_stride, frame_stride, n, stream ? (cudaStream_t)stream : c->s_main);
 }
@@ -660,7 +661,7 @@ int b2c_hysteresis_device(b2c_handle c, int n, uint8_t *dev_edges, size_t edges_
 int b2c_run_batch_host(b2c_handle c, const uint8_t *frames, size_t row_stride, int n, uint8_t *edges_out, int packed_bits)
 {
   if (!c || !frames || !edges_out || c->band || n < 1) return B2C_ERR_INVALID;
-  if (row_stride < (size_t)c->w * 3) return B2C_ERR_SIZE;
+  if (row_stride < (size_t)c->w * c->ch) return B2C_ERR_SIZE;
   DevGuard g(c->dev);
   const int w = c->w, h = c->h;
   const int slot_frames = std::max(1, c->max_batch / NSLOT);
@@ -721,7 +722,7 @@ int b2c_run_batch_host(b2c_handle c, const uint8_t *frames, size_t row_stride, i
       CK(c, cudaMemcpyAsync(din, src, (size_t)cnt * in_frame_host, cudaMemcpyHostToDevice, c->s_h2d));
     } else {
       for (int f = 0; f < cnt; ++f)
-        CK(c, cudaMemcpy2DAsync(din + (size_t)f * c->in_frame_stride, c->in_row_stride, src + (size_t)f * in_frame_host, row_stride, (size_t)w * 3, h, cudaMemcpyHostToDevice, c->s_h2d));
+        CK(c, cudaMemcpy2DAsync(din + (size_t)f * c->in_frame_stride, c->in_row_stride, src + (size_t)f * in_frame_host, row_stride, (size_t)w * c->ch, h, cudaMemcpyHostToDevice, c->s_h2d));
     }
     CK(c, cudaEventRecord(c->ev_in[slot], c->s_h2d));
 

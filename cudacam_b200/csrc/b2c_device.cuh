@@ -41,6 +41,7 @@ struct B2cStencilParams {
   int y0, h_glob;            // global row of row 0 and global image height (zero padding applies
                              // outside [0,h_glob), real neighbour rows are read inside it)
   int nframes;
+  int channels;              // bytes per input pixel: 3 = BGR8, 4 = BGRA8 (alpha ignored), 1 = GRAY8
   uint32_t *map2;            // 2-bit map out
   int map_pitch;             // u32 per row
   long long map_frame_stride;// u32 per frame

@@ -108,6 +108,9 @@ __device__ __forceinline__ void m_nms_item(const B2cStencilParams &p, char *smem
   }
 }
 
+// CH = bytes per input pixel: 3 = BGR8 (the reference's format), 4 = BGRA8 (alpha ignored), 1 = GRAY8 (gray = the byte;
+// the reference's own CV_8UC1 path is broken, SURVEY T13 -- this is what it evidently meant to do)
+template <int CH>
 __global__ void __launch_bounds__(32, MARCH_CTAS_PER_SM) k_stencil_march(const B2cStencilParams p, const int rb)
 {
   B2C_DYN_SMEM(smem);
@@ -132,32 +135,51 @@ __global__ void __launch_bounds__(32, MARCH_CTAS_PER_SM) k_stencil_march(const B
   __syncwarp();
 
   const long long lstride = lane_in ? p.row_stride : 0;
-  const uint8_t *lp = lane_in ? p.bgr + (long long)frame * p.frame_stride + 3 * xl + (long long)Y0 * p.row_stride : p.zeros;
+  const uint8_t *lp = lane_in ? p.bgr + (long long)frame * p.frame_stride + CH * xl + (long long)Y0 * p.row_stride : p.zeros;
 
-  // raw BGR of band-local gray row i (3 x 8 bytes per lane); zero outside the image (cannyEdgeD.cu:91-98)
-  auto load_row = [&](int i, uint2 (&d)[3]) {
+  // raw pixels of band-local gray row i (CH x 8 bytes per lane); zero outside the image (cannyEdgeD.cu:91-98)
+  auto load_row = [&](int i, uint2 (&d)[CH]) {
     const int yg = yg0 + i;
     if (yg >= 0 && yg < p.h_glob && i < ilim) {   // warp-uniform
       const uint2 *q = reinterpret_cast<const uint2 *>(lp + (long long)i * lstride);
-      d[0] = __ldg(q);
-      d[1] = __ldg(q + 1);
-      d[2] = __ldg(q + 2);
+#pragma unroll
+      for (int k = 0; k < CH; ++k) d[k] = __ldg(q + k);
     } else {
-      d[0] = d[1] = d[2] = make_uint2(0u, 0u);
+#pragma unroll
+      for (int k = 0; k < CH; ++k) d[k] = make_uint2(0u, 0u);
     }
   };
   // gray of one row as 4 words of two 16-bit pixels; also kept as bytes in the gray ring for the replay
-  auto gray_row = [&](int i, const uint2 (&d)[3], uint32_t (&m)[4]) {
-    m_mono4(d[0].x, d[0].y, d[1].x, m[0], m[1]);
-    m_mono4(d[1].y, d[2].x, d[2].y, m[2], m[3]);
-    *reinterpret_cast<uint2 *>(smem + MS_GRAY + ((i + 16) & (M_GRING - 1)) * 256 + lane * 8) =
-      make_uint2(__byte_perm(m[0], m[1], 0x6420), __byte_perm(m[2], m[3], 0x6420));
+  auto gray_row = [&](int i, const uint2 (&d)[CH], uint32_t (&m)[4]) {
+    uint2 bytes;
+    if constexpr (CH == 3) {
+      m_mono4(d[0].x, d[0].y, d[1].x, m[0], m[1]);
+      m_mono4(d[1].y, d[2].x, d[2].y, m[2], m[3]);
+      bytes = make_uint2(__byte_perm(m[0], m[1], 0x6420), __byte_perm(m[2], m[3], 0x6420));
+    } else if constexpr (CH == 4) {   // one dp4a per pixel: (B*28 + G*152 + R*76 + A*0), byte 1 of the sum = gray
+      uint32_t t[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        t[2 * k] = __dp4a(d[k].x, 0x004C981Cu, 0u);
+        t[2 * k + 1] = __dp4a(d[k].y, 0x004C981Cu, 0u);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) m[j] = __byte_perm(t[2 * j], t[2 * j + 1], 0x7531);
+      bytes = make_uint2(__byte_perm(m[0], m[1], 0x6420), __byte_perm(m[2], m[3], 0x6420));
+    } else {                          // gray input: the bytes are the gray values
+      bytes = d[0];
+      m[0] = __byte_perm(bytes.x, 0u, 0x4140);
+      m[1] = __byte_perm(bytes.x, 0u, 0x4342);
+      m[2] = __byte_perm(bytes.y, 0u, 0x4140);
+      m[3] = __byte_perm(bytes.y, 0u, 0x4342);
+    }
+    *reinterpret_cast<uint2 *>(smem + MS_GRAY + ((i + 16) & (M_GRING - 1)) * 256 + lane * 8) = bytes;
   };
 
 #if !defined(B2C_EMU)
-  // De-synchronise the warps of an SM: stage A is alu-pipe work, stage C fma-pipe work; warps that start together
-  // stay in the same stage and fight for one pipe while the other idles.  A pseudo-random start delay of up to one
-  // block period spreads the phases (measured: 1.4x on the 64 x 1080p batch).
+  // Optional pseudo-random start delay (option march_stagger_ns, default 0).  Hypothesis: stage A is alu-pipe work,
+  // stage C fma-pipe work, so warps that start together fight for one pipe.  Measured: no effect at any band height
+  // (the warps are not phase-locked) -- kept only as an experiment knob.
   if (p.stagger_ns > 0) {
     const unsigned bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
     __nanosleep(((bid * 2654435761u) >> 24) * (unsigned)p.stagger_ns >> 8);
@@ -165,9 +187,9 @@ __global__ void __launch_bounds__(32, MARCH_CTAS_PER_SM) k_stencil_march(const B
 #endif
   // ---- prologue: gray rows -4 .. -1 into window slots 1 .. 4 -----------------------------------------------
   uint32_t win[5][4];
-  uint2 pre[3];   // raw BGR of the next gray row, in flight while the current row is processed
+  uint2 pre[CH];   // raw pixels of the next gray row, in flight while the current row is processed
   {
-    uint2 d[3];
+    uint2 d[CH];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       load_row(-4 + k, d);
@@ -188,7 +210,7 @@ __global__ void __launch_bounds__(32, MARCH_CTAS_PER_SM) k_stencil_march(const B
 #if !defined(B2C_EMU) && !defined(B2C_MARCH_NO_L2PF)
     // pull the gray rows of the NEXT block (768 B per row and strip = 7 lines of 128 B) into L2 while this block
     // computes: 4 rows per instruction (lanes 7q .. 7q+6 take row q), 3 instructions for 12 rows
-    if (lane < 28) {
+    if (CH == 3 && lane < 28) {   // (only for the 3-byte format: 7 lines per strip row)
       const int q = lane / 7;
       const long long xoff = (long long)(X0 - 8) * 3 + (lane - 7 * q) * 128;
       if (xoff >= 0 && xoff < (long long)p.w * 3) {
@@ -211,7 +233,9 @@ __global__ void __launch_bounds__(32, MARCH_CTAS_PER_SM) k_stencil_march(const B
       for (int k = 0; k < 5; ++k) {
         const int rr = half * 5 + k;   // row within the block
         const int b = b0 + rr, g = b + 2;
-        uint2 cur[3] = { pre[0], pre[1], pre[2] };
+        uint2 cur[CH];
+#pragma unroll
+        for (int q = 0; q < CH; ++q) cur[q] = pre[q];
         load_row(g + 1, pre);
         gray_row(g, cur, win[k]);
         const uint32_t(&a0)[4] = win[(k + 1) % 5], (&a1)[4] = win[(k + 2) % 5], (&a2)[4] = win[(k + 3) % 5], (&a3)[4] = win[(k + 4) % 5], (&a4)[4] = win[k];
@@ -400,11 +424,19 @@ inline int march_emu_launch(const B2cStencilParams &p, int rb)
 {
   if (p.w % 8 || p.row_stride % 8 || p.frame_stride % 8 || (reinterpret_cast<uintptr_t>(p.bgr) & 7)) return -2;
   dim3 grid((p.w + MT_X - 1) / MT_X, (p.h + rb - 1) / rb, p.nframes);
-  emu::launch(grid, dim3(32), MARCH_SMEM, false, [p, rb] { k_stencil_march(p, rb); });
+  if (p.channels == 1) emu::launch(grid, dim3(32), MARCH_SMEM, false, [p, rb] { k_stencil_march<1>(p, rb); });
+  else if (p.channels == 4) emu::launch(grid, dim3(32), MARCH_SMEM, false, [p, rb] { k_stencil_march<4>(p, rb); });
+  else emu::launch(grid, dim3(32), MARCH_SMEM, false, [p, rb] { k_stencil_march<3>(p, rb); });
   return 0;
 }
 #else
-inline cudaError_t march_configure() { return cudaFuncSetAttribute(k_stencil_march, cudaFuncAttributeMaxDynamicSharedMemorySize, MARCH_SMEM); }
+inline cudaError_t march_configure()
+{
+  cudaError_t e = cudaFuncSetAttribute(k_stencil_march<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MARCH_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_stencil_march<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MARCH_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_stencil_march<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, MARCH_SMEM);
+  return e;
+}
 // 8-byte aligned rows and whole lanes (w % 8 == 0); anything else goes through the tile kernel
 inline bool march_supported(const B2cStencilParams &p)
 {
@@ -434,7 +466,9 @@ inline cudaError_t march_launch(const B2cStencilParams &p, int sm_count, int rb_
 {
   const int rb = rb_override > 0 ? rb_override : march_band_rows(p.w, p.h, p.nframes, sm_count);
   dim3 grid((p.w + MT_X - 1) / MT_X, (p.h + rb - 1) / rb, p.nframes);
-  k_stencil_march<<<grid, 32, MARCH_SMEM, st>>>(p, rb);
+  if (p.channels == 1) k_stencil_march<1><<<grid, 32, MARCH_SMEM, st>>>(p, rb);
+  else if (p.channels == 4) k_stencil_march<4><<<grid, 32, MARCH_SMEM, st>>>(p, rb);
+  else k_stencil_march<3><<<grid, 32, MARCH_SMEM, st>>>(p, rb);
   return cudaGetLastError();
 }
 #endif

@@ -38,8 +38,7 @@ enum {
   B2C_ERR_NOMEM = -3,
   B2C_ERR_SIZE = -4,        /* frame geometry differs from the one given at creation
                                (reference: logs and carries on with stale data, cannyEdgeH.cu:124-130)  */
-  B2C_ERR_UNSUPPORTED = -5, /* e.g. channels != 3: the reference's CV_8UC1 path is broken
-                               (cannyEdgeH.cu:140-146 then :60-64 overwrite it), so it is rejected      */
+  B2C_ERR_UNSUPPORTED = -5, /* e.g. channels not in {1, 3, 4}, or an option that a mode does not support          */
   B2C_ERR_STATE = -6        /* accessor used before any frame was run                                   */
 };
 
@@ -60,7 +59,10 @@ enum {
                          (cannyEdgeH.cu:154-212) for the stage passed to the last b2c_run  */
 };
 
-/* ---- lifetime: cvp::cuda::CannyEdge::CannyEdge / ~CannyEdge (cannyEdgeH.cu:16-47), _initAlloc/_endAlloc (:340-407) */
+/* ---- lifetime: cvp::cuda::CannyEdge::CannyEdge / ~CannyEdge (cannyEdgeH.cu:16-47), _initAlloc/_endAlloc (:340-407)
+ * channels = bytes per pixel of the input frames: 3 = BGR8 (what the reference processes), 4 = BGRA8 (alpha ignored),
+ * 1 = GRAY8 (the gray value is the byte: what the reference's CV_8UC1 path evidently meant to do -- upstream it
+ * uploads the frame to d_mono and then overwrites it with rgb2mono of a stale d_rgb, cannyEdgeH.cu:140-146 + :60-64). */
 B2C_API int b2c_create(b2c_handle *out, int device, int width, int height, int channels, int max_batch);
 B2C_API void b2c_destroy(b2c_handle h);
 

@@ -76,7 +76,7 @@ public:
   // Reference: CannyEdge(unsigned pbo, unsigned w, unsigned h, unsigned nbChannels) (cannyEdgeH.hpp:20).  The GL
   // buffer id is kept only so call sites compile; the bytes the reference copies into the PBO are served by view().
   CannyEdge(unsigned int pbo, unsigned int inputWidth, unsigned int inputHeight, unsigned int inputNbChannels, int device = 0, int maxBatch = 1)
-      : m_pbo(pbo), m_w((int)inputWidth), m_h((int)inputHeight)
+      : m_pbo(pbo), m_w((int)inputWidth), m_h((int)inputHeight), m_ch((int)inputNbChannels)
   {
     const int rc = b2c_create(&m_h_, device, m_w, m_h, (int)inputNbChannels, maxBatch);
     if (rc != B2C_OK) throw b2c::Error(rc, "b2c_create");
@@ -138,6 +138,7 @@ public:
   b2c_handle handle() const { return m_h_; }
   int width() const { return m_w; }
   int height() const { return m_h; }
+  int channels() const { return m_ch; }
 
 private:
   void check(int rc, const char *what) const
@@ -151,7 +152,7 @@ private:
     return v;
   }
   unsigned int m_pbo;
-  int m_w, m_h;
+  int m_w, m_h, m_ch;
   b2c_handle m_h_ = nullptr;
 };
 }// namespace cuda
@@ -168,14 +169,15 @@ public:
   cvPipeline(const cvPipeline &) = delete;
   cvPipeline &operator=(const cvPipeline &) = delete;
 
-  // cvPipeline.cpp:19-41: false for a null implementation, an empty frame or a type other than 8-bit 1/3 channels;
-  // the 1-channel path of the reference is broken and is refused here as well.
+  // cvPipeline.cpp:19-41: false for a null implementation, an empty frame or a type other than 8-bit 1/3 channels.
+  // The frame must have the channel count given to the constructor: 3 (BGR8), 1 (GRAY8 -- works here; upstream the
+  // 1-channel upload is overwritten) or 4 (BGRA8, an addition).
   template <class Mat> bool process(const Mat &inputImage, CannyStage finalStage)
   {
     if (!m_cudaCannyEdge) return false;
     const b2c::FrameView f = b2c::view_of(inputImage);
     if (f.empty()) return false;
-    if (f.channels() != 3) return false;
+    if (f.channels() != m_cudaCannyEdge->channels()) return false;
     m_cudaCannyEdge->run(f, finalStage);
     return true;
   }

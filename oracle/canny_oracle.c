@@ -282,16 +282,39 @@ ORACLE_API void oracle_set_high(const uint8_t *low, uint8_t *high, uint8_t v) { 
 
 /* Whole path, src/cvp/cannyEdgeH.cu:49-120 with finalStage = HYSTER.  Any output pointer may be NULL.
  * All outputs are tightly packed w*h. */
+/* channels = bytes per pixel: 3 = BGR8 (the reference), 4 = BGRA8 (same weights on bytes 0..2, byte 3 ignored),
+ * 1 = GRAY8 (mono = the byte; the reference accepts CV_8UC1 in cvPipeline.cpp:32 but its upload is overwritten,
+ * cannyEdgeH.cu:140-146 + :60-64, so there is no reference output to match -- this is the evident intent) */
+ORACLE_API int oracle_canny_ch(const uint8_t *pix, size_t stride, int w, int h, int channels, uint8_t low, uint8_t high,
+                               uint8_t *mono_o, uint8_t *blur_o, float *grad_o, uint8_t *sector_o, uint8_t *nms_o,
+                               uint8_t *thresh_o, uint8_t *edges_o);
+
 ORACLE_API int oracle_canny(const uint8_t *bgr, size_t stride, int w, int h, uint8_t low, uint8_t high,
                             uint8_t *mono_o, uint8_t *blur_o, float *grad_o, uint8_t *sector_o, uint8_t *nms_o,
                             uint8_t *thresh_o, uint8_t *edges_o)
 {
+  return oracle_canny_ch(bgr, stride, w, h, 3, low, high, mono_o, blur_o, grad_o, sector_o, nms_o, thresh_o, edges_o);
+}
+
+ORACLE_API int oracle_canny_ch(const uint8_t *bgr, size_t stride, int w, int h, int channels, uint8_t low, uint8_t high,
+                               uint8_t *mono_o, uint8_t *blur_o, float *grad_o, uint8_t *sector_o, uint8_t *nms_o,
+                               uint8_t *thresh_o, uint8_t *edges_o)
+{
+  if (channels != 1 && channels != 3 && channels != 4) return -2;
   const size_t n = (size_t)w * h;
   uint8_t *mono = (uint8_t *)malloc(n), *blur = (uint8_t *)malloc(n), *nms = (uint8_t *)malloc(n), *th = (uint8_t *)malloc(n);
   float *sx = (float *)malloc(n * 4), *sy = (float *)malloc(n * 4), *grad = (float *)malloc(n * 4);
   int16_t *gx = (int16_t *)malloc(n * 2), *gy = (int16_t *)malloc(n * 2);
   if (!mono || !blur || !nms || !th || !sx || !sy || !grad || !gx || !gy) return -1;
-  oracle_rgb2mono(bgr, stride, w, h, mono);
+  if (channels == 3) oracle_rgb2mono(bgr, stride, w, h, mono);
+  else
+    for (int y = 0; y < h; ++y) {
+      const uint8_t *q = bgr + (size_t)y * stride;
+      for (int x = 0; x < w; ++x) {
+        int v = channels == 1 ? q[x] : (q[4 * x] * B_WT + q[4 * x + 1] * G_WT + q[4 * x + 2] * R_WT) >> 6;
+        mono[(size_t)y * w + x] = (uint8_t)(v > 255 ? 255 : v);
+      }
+    }
   oracle_gaussian(mono, w, h, blur);
   oracle_sobel(blur, w, h, sx, sy, gx, gy);
   oracle_grad(sx, sy, n, grad);

@@ -23,7 +23,9 @@ static void fill_gk(float gk[25])
   }
 }
 
+static int g_emu_channels = 3;
 extern "C" {
+__attribute__((visibility("default"))) void emu_set_channels(int ch) { g_emu_channels = ch; }
 // impl: 1 = tile kernel (EMIT when any stage pointer is given), 0 = fused CTA-tile kernel, 100 + rb = marching kernel with rb rows per band
 __attribute__((visibility("default"))) int emu_stencil(int impl, const uint8_t *bgr, long long row_stride, long long frame_stride, int w, int h, int y0, int h_glob, int nframes,
                                                        unsigned lo, unsigned hi, uint32_t *map2, uint8_t *mono, uint8_t *blur, float *grad, uint8_t *nms, uint8_t *thresh)
@@ -33,7 +35,7 @@ __attribute__((visibility("default"))) int emu_stencil(int impl, const uint8_t *
   alignas(16) static const uint8_t zeros[256] = { 0 };
   p.zeros = zeros;
   p.bgr = bgr; p.row_stride = row_stride; p.frame_stride = frame_stride;
-  p.w = w; p.h = h; p.y0 = y0; p.h_glob = h_glob; p.nframes = nframes;
+  p.w = w; p.h = h; p.y0 = y0; p.h_glob = h_glob; p.nframes = nframes; p.channels = g_emu_channels;
   p.map2 = map2; p.map_pitch = (w + 15) / 16; p.map_frame_stride = (long long)h * p.map_pitch;
   p.lo = lo; p.hi = hi;
   fill_gk(p.gk);
@@ -56,6 +58,7 @@ __attribute__((visibility("default"))) int emu_stencil(int impl, const uint8_t *
   }
 #ifdef B2C_EMU_FUSED
   if (impl >= 100) return b2c::march_emu_launch(p, impl - 100);   // impl = 100 + rows per band
+  if (p.channels != 3) return -3;
   return b2c::fused_emu_launch(p);
 #else
   return -1;

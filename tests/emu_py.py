@@ -32,6 +32,8 @@ def lib():
         _lib = C.CDLL(EMU_SO)
         _lib.emu_stencil.restype = _i
         _lib.emu_stencil.argtypes = [_i, _vp, _ll, _ll, _i, _i, _i, _i, _i, C.c_uint, C.c_uint, _vp, _vp, _vp, _vp, _vp, _vp]
+        _lib.emu_set_channels.restype = None
+        _lib.emu_set_channels.argtypes = [_i]
         _lib.emu_hysteresis.restype = _i
         _lib.emu_hysteresis.argtypes = [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, C.POINTER(_i)]
     return _lib
@@ -42,7 +44,7 @@ def stencil(bgr, lo=10, hi=40, impl=1, stages=False, y0=0, h_glob=None, rows=Non
     a = np.ascontiguousarray(bgr, np.uint8)
     if a.ndim == 3:
         a = a[None]
-    n, hh, w, _ = a.shape
+    n, hh, w, ch = a.shape
     h = hh if rows is None else rows
     h_glob = hh if h_glob is None else h_glob
     gpr = (w + 15) // 16
@@ -54,7 +56,11 @@ def stencil(bgr, lo=10, hi=40, impl=1, stages=False, y0=0, h_glob=None, rows=Non
                    nms=np.zeros((h, w), np.uint8), thresh=np.zeros((h, w), np.uint8))
         ptrs = [out[k].ctypes.data for k in ("mono", "blur", "grad", "nms", "thresh")]
     base = a.ctypes.data + row0 * a.strides[1]
-    rc = lib().emu_stencil(impl, base, a.strides[1], a.strides[0], w, h, y0, h_glob, n, lo, hi, map2.ctypes.data, *ptrs)
+    lib().emu_set_channels(ch)
+    try:
+        rc = lib().emu_stencil(impl, base, a.strides[1], a.strides[0], w, h, y0, h_glob, n, lo, hi, map2.ctypes.data, *ptrs)
+    finally:
+        lib().emu_set_channels(3)
     assert rc == 0, rc
     return out
 
@@ -73,10 +79,14 @@ def hysteresis(map2, w, grid_blocks=3, tile_rows=4, ghost_top=None, ghost_bot=No
     return edges, bits, rounds, ch.value
 
 
-def stencil_raw(buf, row0, w, h, lo=10, hi=40, impl=0, y0=0, h_glob=None):
-    """buf: 2-D uint8 array of padded rows; the frame starts at row `row0`.  Returns the 2-bit map or None if the
-    implementation is not available in the emulator build."""
+def stencil_raw(buf, row0, w, h, lo=10, hi=40, impl=0, y0=0, h_glob=None, channels=3):
+    """buf: 2-D uint8 array of padded rows (w * channels bytes used per row); the frame starts at row `row0`.  Returns
+    the 2-bit map or None if the implementation is not available in the emulator build."""
     h_glob = h if h_glob is None else h_glob
     map2 = np.zeros((h, (w + 15) // 16), np.uint32)
-    rc = lib().emu_stencil(impl, buf.ctypes.data + row0 * buf.strides[0], buf.strides[0], 0, w, h, y0, h_glob, 1, lo, hi, map2.ctypes.data, None, None, None, None, None)
+    lib().emu_set_channels(channels)
+    try:
+        rc = lib().emu_stencil(impl, buf.ctypes.data + row0 * buf.strides[0], buf.strides[0], 0, w, h, y0, h_glob, 1, lo, hi, map2.ctypes.data, None, None, None, None, None)
+    finally:
+        lib().emu_set_channels(3)
     return map2 if rc == 0 else None

@@ -16,6 +16,8 @@ def _load_oracle():
     lib = C.CDLL(ORACLE_SO)
     lib.oracle_canny.restype = _i
     lib.oracle_canny.argtypes = [_vp, _sz, _i, _i, C.c_uint8, C.c_uint8] + [_vp] * 7
+    lib.oracle_canny_ch.restype = _i
+    lib.oracle_canny_ch.argtypes = [_vp, _sz, _i, _i, _i, C.c_uint8, C.c_uint8] + [_vp] * 7
     lib.oracle_hysteresis.restype = None
     lib.oracle_hysteresis.argtypes = [_vp, _i, _i, _vp]
     lib.oracle_hysteresis_launches.restype = _i
@@ -46,11 +48,13 @@ def oracle():
 def canny(bgr, low=10, high=40, want_edges=True):
     """Runs the CPU restatement.  Returns dict(mono, blur, grad, sector, nms, thresh, edges)."""
     bgr = np.ascontiguousarray(bgr, np.uint8)
-    h, w, _ = bgr.shape
+    if bgr.ndim == 2:
+        bgr = bgr[:, :, None]
+    h, w, ch = bgr.shape
     out = dict(mono=np.empty((h, w), np.uint8), blur=np.empty((h, w), np.uint8), grad=np.empty((h, w), np.float32),
                sector=np.empty((h, w), np.uint8), nms=np.empty((h, w), np.uint8), thresh=np.empty((h, w), np.uint8),
                edges=np.empty((h, w), np.uint8))
-    rc = oracle().oracle_canny(bgr.ctypes.data, bgr.strides[0], w, h, low, high, out["mono"].ctypes.data, out["blur"].ctypes.data,
+    rc = oracle().oracle_canny_ch(bgr.ctypes.data, bgr.strides[0], w, h, ch, low, high, out["mono"].ctypes.data, out["blur"].ctypes.data,
                                out["grad"].ctypes.data, out["sector"].ctypes.data, out["nms"].ctypes.data, out["thresh"].ctypes.data,
                                out["edges"].ctypes.data if want_edges else None)
     assert rc == 0

@@ -46,7 +46,7 @@ def test_argument_errors_without_gpu():
     from cudacam_b200 import _lib
     h = C.c_void_p()
     assert _lib.lib.b2c_create(C.byref(h), 0, 0, 10, 3, 1) == _lib.ERR_INVALID
-    assert _lib.lib.b2c_create(C.byref(h), 0, 64, 48, 1, 1) == _lib.ERR_UNSUPPORTED   # CV_8UC1 is broken in the reference (T13)
+    assert _lib.lib.b2c_create(C.byref(h), 0, 64, 48, 2, 1) == _lib.ERR_UNSUPPORTED   # channels must be 1 (GRAY8), 3 (BGR8) or 4 (BGRA8)
     assert _lib.lib.b2c_create(None, 0, 64, 48, 3, 1) == _lib.ERR_INVALID
     assert _lib.lib.b2c_run(None, None, 0, 5) == _lib.ERR_INVALID
     assert _lib.lib.b2c_get_low_threshold(None) == _lib.ERR_INVALID

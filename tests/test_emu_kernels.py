@@ -176,3 +176,31 @@ def test_march_geometry_corner_cases(w, h, rb):
     buf[4:4 + h, :w * 3] = f.reshape(h, w * 3)
     e = E.stencil_raw(buf, 4, w, h, 10, 40, impl=100 + rb)
     assert e is not None and np.array_equal(e, O.thresh_to_map2(r["thresh"]))
+
+
+def _to_format(f, ch):
+    """BGR frame -> GRAY8 (green channel as the gray picture) or BGRA8 (random alpha, must be ignored)."""
+    if ch == 1:
+        return np.ascontiguousarray(f[:, :, 1:2])
+    a = np.random.default_rng(1).integers(0, 256, f.shape[:2] + (1,), dtype=np.uint8)
+    return np.ascontiguousarray(np.concatenate([f, a], axis=2))
+
+
+@pytest.mark.parametrize("ch", [1, 4])
+@pytest.mark.parametrize("kind,w,h,seed", [("scene", 200, 60, 7), ("steps", 256, 45, 9), ("noise", 96, 30, 8)])
+def test_other_input_formats(kind, w, h, seed, ch):
+    """GRAY8 and BGRA8 front ends of the marching and the tile kernel; BGRA must equal BGR, gray must
+    equal the oracle run on the gray picture."""
+    f = synth.frame(kind, seed, w, h)
+    g = _to_format(f, ch)
+    r = O.canny(g)
+    if ch == 4:
+        assert np.array_equal(r["thresh"], O.canny(f)["thresh"])
+    e = E.stencil(g, impl=1, stages=True)
+    for k in ("mono", "blur", "nms", "thresh"):
+        assert np.array_equal(e[k], r[k]), k
+    stride = (w * ch + 15) // 16 * 16
+    buf = np.zeros((h + 8, stride), np.uint8)
+    buf[4:4 + h, :w * ch] = g.reshape(h, w * ch)
+    m = E.stencil_raw(buf, 4, w, h, impl=126, channels=ch)
+    assert m is not None and np.array_equal(m, O.thresh_to_map2(r["thresh"]))

@@ -164,3 +164,23 @@ def test_full_size_properties_1080p_batch():
             t2 = np.where(got[i] == 255, 255, np.where(th == 128, 128, 0)).astype(np.uint8)
             assert np.array_equal(O.hysteresis(t2), got[i])
     assert np.array_equal(got[0], got[4])   # frames 0 and 4 are the same picture
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["march", "tile"])
+@pytest.mark.parametrize("ch", [1, 4])
+def test_other_input_formats(ch, impl):
+    """GRAY8 and BGRA8 input: single frame with all accessors, and the batch pipeline."""
+    w, h = 648, 360
+    f = synth.frame("scene", 21, w, h)
+    if ch == 1:
+        g = np.ascontiguousarray(f[:, :, 1:2])
+    else:
+        g = np.ascontiguousarray(np.concatenate([f, np.random.default_rng(1).integers(0, 256, (h, w, 1), dtype=np.uint8)], axis=2))
+    r = O.canny(g)
+    if ch == 4:
+        assert np.array_equal(r["edges"], O.canny(f)["edges"])   # alpha is ignored
+    with cb.CannyEdge(w, h, channels=ch, max_batch=3) as c:
+        c.set_option("stencil_impl", impl)
+        _check_all(c, g, r)
+        got = c.run_batch(np.stack([g, g, g]))
+        assert np.array_equal(got[1], r["edges"])
