@@ -106,7 +106,7 @@ allsass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=T
 keep, on = [], False
 for line in allsass.split("\n"):
     if "Function :" in line:
-        on = "k_stencil_march" in line
+        on = "k_stencil_march" in line and "ILi3E" in line   # the BGR8 instance
     if on:
         keep.append(line)
 open(os.path.join(P, f"{TAG}_k_stencil_march.sass"), "w").write("\n".join(keep) + "\n")
