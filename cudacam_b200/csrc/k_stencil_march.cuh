@@ -200,7 +200,9 @@ __global__ void __launch_bounds__(32, MARCH_CTAS_PER_SM) k_stencil_march(const B
   // Sobel row state (rows are consumed in order): Dp = D(r-1), PX = D(r-2) + 2 D(r-1), Ta = T(r-2), Tb = T(r-1)
   uint32_t Dp[4] = { 0, 0, 0, 0 }, PX[4] = { 0, 0, 0, 0 }, Ta[4] = { 0, 0, 0, 0 }, Tb[4] = { 0, 0, 0, 0 };
   uint32_t cand_carry = 0u;   // candidate bits of the last Sobel row of the previous chunk
-  const float negl = -p.n_lo[0];
+  // -N_low through a shuffle: the value is warp-uniform, and left in a uniform register it is copied into a vector
+  // register once per FHFMA chain (8 copies per row); a shuffle result lives in a vector register
+  const float negl = __shfl_sync(B2C_FULL, -p.n_lo[0], 0);
   const uint32_t cmask = out_lane ? 0xFFu : 0u;
 
   const int nblocks = (rows_out + 4 + MK - 1) / MK;
