@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200canny.so")
+LIB_PATH = os.environ.get("B2C_LIB_PATH") or os.path.join(_HERE, "libb200canny.so")   # (override: profiling builds of the same library)
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_SIZE, ERR_UNSUPPORTED, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
 STAGE_MONO, STAGE_GAUSSIAN, STAGE_GRADIENT, STAGE_NMS, STAGE_THRESH, STAGE_HYSTER = range(6)

@@ -25,7 +25,6 @@
 #include "k_hysteresis.cuh"
 #include "k_hysteresis_uf.cuh"
 #include "k_band_p2p.cuh"
-#include "k_stencil_fused.cuh"
 #include "k_stencil_march.cuh"
 #include "k_stencil_tile.cuh"
 #include "k_views.cuh"
@@ -45,9 +44,10 @@ struct b2c_ctx {
   int sm_count = 0;
   uint8_t lo = 10, hi = 40;   // src/cvp/cannyEdgeH.cu:22-23
   bool profiling = true;      // src/cvp/cannyEdgeH.cu:24
-  int stencil_impl = 0;       // 0 marching warp-per-strip kernel, 1 staged tile kernel, 2 fused CTA-tile kernel
+  int stencil_impl = 0;       // 0 marching two-warp pipeline kernel, 1 staged tile kernel (all-stages path)
   int march_rb = 0;           // rows per band of the marching kernel, 0 = automatic
-  int march_stagger_ns = 0;   // experiment knob, see k_stencil_march.cuh
+  int march_ctas_per_sm = 0;  // resident CTAs per SM of the marching kernel (occupancy query at creation)
+  int march_extra_smem = 0;   // profiling knob: extra dynamic shared memory per CTA (lowers the occupancy)
   int hyst_impl = 0;          // 0 union-find as 3 launches (tile, border, resolve), 1 tile rounds (cooperative), 2 union-find as one cooperative launch
   int hyst_tile_rows = 16;
   int uf_spread = 1;
@@ -215,8 +215,8 @@ int alloc_common(b2c_ctx *c)
   CK(c, cudaFuncSetAttribute(b2c::k_uf_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, b2c::UT_SMEM));
   CK(c, cudaFuncSetAttribute(b2c::k_stencil_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2c::TILE_SMEM));
   CK(c, cudaFuncSetAttribute(b2c::k_stencil_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2c::TILE_SMEM));
-  if (b2c::march_configure() != cudaSuccess) return set_err(c, cudaGetLastError(), "march_configure");
-  return b2c::fused_configure() == cudaSuccess ? B2C_OK : set_err(c, cudaGetLastError(), "fused_configure");
+  if (b2c::march_configure(&c->march_ctas_per_sm) != cudaSuccess) return set_err(c, cudaGetLastError(), "march_configure");
+  return B2C_OK;
 }
 
 void fill_stencil_params(b2c_ctx *c, B2cStencilParams &p, const uint8_t *bgr, size_t row_stride, size_t frame_stride, int n)
@@ -238,16 +238,9 @@ void fill_stencil_params(b2c_ctx *c, B2cStencilParams &p, const uint8_t *bgr, si
   p.lo = c->lo;
   p.hi = c->hi;
   fill_gk(p.gk);
-  for (int k = 0; k < 3; ++k) {
-    const float a = (float)(256 * k + c->lo + 1), b = (float)(256 * k + c->hi + 1);
-    p.n_lo[k] = ldexpf(4.0f * a * a, -48);   // exact: < 2^24
-    p.n_hi[k] = ldexpf(4.0f * b * b, -48);   // fused kernel: sums carry the fp16-subnormal scale 2^-24
-  }
-  p.n_wrap[0] = ldexpf(262144.0f, -48);    // 4*256^2
-  p.n_wrap[1] = ldexpf(1048576.0f, -48);   // 4*512^2
+  b2c_fill_thresholds(p);
   p.pitch8 = c->pitch8;
   p.pitchf = c->pitchf;
-  p.stagger_ns = c->march_stagger_ns;
 }
 
 // Fused stencil: BGR8 -> 2-bit map for n frames.
@@ -256,11 +249,8 @@ int launch_stencil(b2c_ctx *c, const uint8_t *bgr, size_t row_stride, size_t fra
   B2cStencilParams p;
   fill_stencil_params(c, p, bgr, row_stride, frame_stride, n);
   if (c->stencil_impl == 0 && b2c::march_supported(p)) {
-    cudaError_t e = b2c::march_launch(p, c->sm_count, c->march_rb, st);
+    cudaError_t e = b2c::march_launch(p, c->sm_count, c->march_ctas_per_sm, c->march_rb, st, c->march_extra_smem);
     if (e != cudaSuccess) return set_err(c, e, "k_stencil_march launch");
-  } else if (c->stencil_impl == 2 && c->ch == 3 && b2c::fused_supported(p)) {
-    cudaError_t e = b2c::fused_launch(p, c->sm_count, st);
-    if (e != cudaSuccess) return set_err(c, e, "k_stencil_fused launch");
   } else {
     dim3 grid((c->w + b2c::TILE_W - 1) / b2c::TILE_W, (c->rows_alloc + b2c::TILE_H - 1) / b2c::TILE_H, n);
     b2c::k_stencil_tile<false><<<grid, b2c::TILE_THREADS, b2c::TILE_SMEM, st>>>(p);
@@ -426,7 +416,7 @@ int b2c_create(b2c_handle *out, int device, int width, int height, int channels,
   c->max_batch = max_batch;
   c->rows_alloc = height;
   DevGuard g(device);
-  c->in_row_stride = round_up((size_t)width * channels, 16);
+  c->in_row_stride = round_up(round_up((size_t)width, 8) * channels, 16);   // whole 8-pixel lanes are backed by memory
   c->in_frame_stride = c->in_row_stride * height;
   int rc = alloc_common(c);
   if (rc == B2C_OK && cudaMalloc(&c->d_in, (size_t)max_batch * c->in_frame_stride) != cudaSuccess) rc = set_err(c, cudaGetLastError(), "cudaMalloc(d_in)");
@@ -1126,13 +1116,8 @@ int b2c_set_option(b2c_handle c, const char *name, int value)
 {
   if (!c || !name) return B2C_ERR_INVALID;
   if (!strcmp(name, "stencil_impl")) {
-    if (value < 0 || value > 2) return B2C_ERR_INVALID;
+    if (value < 0 || value > 1) return B2C_ERR_INVALID;
     c->stencil_impl = value;
-    return B2C_OK;
-  }
-  if (!strcmp(name, "march_stagger_ns")) {
-    if (value < 0) return B2C_ERR_INVALID;
-    c->march_stagger_ns = value;
     return B2C_OK;
   }
   if (!strcmp(name, "uf_spread")) {
@@ -1143,6 +1128,11 @@ int b2c_set_option(b2c_handle c, const char *name, int value)
     c->hyst_phase_timing = value != 0;
     if (c->hyst_phase_timing && !c->ev_h[0])
       for (auto &e : c->ev_h) CK(c, cudaEventCreate(&e));
+    return B2C_OK;
+  }
+  if (!strcmp(name, "march_extra_smem")) {
+    if (value < 0 || value > 64 * 1024) return B2C_ERR_INVALID;
+    c->march_extra_smem = value;
     return B2C_OK;
   }
   if (!strcmp(name, "march_rb")) {
@@ -1189,6 +1179,8 @@ int b2c_get_info(b2c_handle c, const char *name)
   if (!strcmp(name, "hyst_grid")) return c->hyst_grid;
   if (!strcmp(name, "sm_count")) return c->sm_count;
   if (!strcmp(name, "stencil_impl")) return c->stencil_impl;
+  if (!strcmp(name, "march_ctas_per_sm")) return c->march_ctas_per_sm;
+  if (!strcmp(name, "march_band_rows")) return c->march_rb > 0 ? c->march_rb : b2c::march_band_rows(c->w, c->rows_alloc, c->max_batch, c->sm_count, c->march_ctas_per_sm);
   if (!strcmp(name, "in_row_stride")) return (int)c->in_row_stride;
   if (!strcmp(name, "plane_pitch_words")) return c->plane_pitch;
   if (!strcmp(name, "map_pitch_words")) return c->map_pitch;

@@ -13,6 +13,7 @@
 //                     (src/cvp/cannyEdgeD.cu:379-395).
 #pragma once
 #include <stdint.h>
+#include <math.h>
 
 #ifdef B2C_EMU
 #include "cuda_emu.h"
@@ -50,13 +51,13 @@ struct B2cStencilParams {
   // double threshold in the N = sumX^2+sumY^2 domain.  The reference thresholds v = (unsigned char)grad
   // (cannyEdgeD.cu:267,290), grad = 0.5*sqrt(N); the cast wraps mod 256, and trunc(grad) >= m <=> N >= 4m^2, so
   //   v > T  <=>  N in [n[0], 4*256^2) or [n[1], 4*512^2) or [n[2], inf),  n[k] = 4*(256k + T + 1)^2
-  // The fused kernel works on fp16-subnormal-scaled sums (x 2^-24), so its N is scaled by 2^-48: n_scale.
+  // The marching kernel works on Sobel sums scaled by 2^-12 (fp16 normal numbers), so its N is scaled by 2^-24.
   float n_lo[3], n_hi[3], n_wrap[2];
+  uint32_t n_pre;            // fp16x2: candidate pre-filter threshold on N' = fl16(gx'^2 + gy'^2), see b2c_fill_thresholds
   // optional per-stage outputs (frame 0 only; null = not written)
   uint8_t *mono, *blur, *nms, *thresh;
   float *grad;
   int pitch8, pitchf;        // in elements
-  int stagger_ns;            // marching kernel: maximum start delay of a warp (phase spreading), 0 = none
 };
 
 struct B2cHystParams {
@@ -80,6 +81,35 @@ struct B2cHystParams {
   int *parent;               // union-find parents, one int per pixel of the padded plane (only weak pixels are used)
   long long parent_frame_stride;
 };
+
+// Largest fp16 <= v (v >= 0, below the fp16 range limit), as its bit pattern.
+static inline uint16_t b2c_f2h_rd(float v)
+{
+  if (!(v > 0.0f)) return 0;
+  int e;
+  const float m = frexpf(v, &e);   // v = m * 2^e, m in [0.5, 1)
+  const int E = e - 1;             // v = (2m) * 2^E
+  if (E < -14) return (uint16_t)floorf(ldexpf(v, 24));   // subnormal: multiples of 2^-24
+  const uint32_t mant = (uint32_t)floorf(ldexpf(2.0f * m - 1.0f, 10));
+  return (uint16_t)(((uint32_t)(E + 15) << 10) | mant);
+}
+// Thresholds of the marching kernel from low / high (p.lo, p.hi must be set): N = sumX^2 + sumY^2 scaled by 2^-24.
+// The packed pre-filter computes N' = fl16(gy'^2 + fl16(gx'^2)) with gx' = sumX * 2^-12: each rounding is relative
+// <= 2^-11 or, for subnormal results, absolute <= 2^-25, so N' >= N 2^-24 (1 - 2^-10) - 2^-24: the threshold below
+// never rejects a pixel with N >= N_low.
+static inline void b2c_fill_thresholds(B2cStencilParams &p)
+{
+  for (int k = 0; k < 3; ++k) {
+    const float a = (float)(256 * k + p.lo + 1), b = (float)(256 * k + p.hi + 1);
+    p.n_lo[k] = ldexpf(4.0f * a * a, -24);   // exact: < 2^24
+    p.n_hi[k] = ldexpf(4.0f * b * b, -24);
+  }
+  p.n_wrap[0] = ldexpf(262144.0f, -24);    // 4*256^2
+  p.n_wrap[1] = ldexpf(1048576.0f, -24);   // 4*512^2
+  const float nlow = 4.0f * (float)(p.lo + 1) * (float)(p.lo + 1);
+  const uint32_t h = b2c_f2h_rd(ldexpf(nlow * (1.0f - 1.0f / 1024.0f) - 1.0f, -24));
+  p.n_pre = h | (h << 16);
+}
 
 // ---- packed fp16x2 helpers (operands are the raw 32-bit patterns) -------------------------------------------
 // All values that pass through them are integers of magnitude <= 2048, which fp16 represents exactly, so

@@ -13,7 +13,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -56,7 +58,28 @@ struct Grid {
   std::barrier<> bar;
   explicit Grid(int nblocks) : bar(nblocks) {}
 };
+// named barrier (PTX bar.sync / bar.arrive with an id and a thread count): completes when `n` threads have arrived,
+// arrivers do not wait
+struct NamedBar {
+  std::mutex m;
+  std::condition_variable cv;
+  int count = 0;
+  unsigned gen = 0;
+  void arrive(int n, bool wait)
+  {
+    std::unique_lock<std::mutex> l(m);
+    const unsigned g = gen;
+    if (++count == n) {
+      count = 0;
+      ++gen;
+      cv.notify_all();
+    } else if (wait) {
+      cv.wait(l, [&] { return gen != g; });
+    }
+  }
+};
 struct Block {
+  NamedBar named[16];
   dim3 gridDim, blockDim;
   uint3e blockIdx;
   std::unique_ptr<std::barrier<>> bar;
@@ -126,6 +149,29 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, bool cooperative, F body)
 }
 
 inline void grid_sync();
+inline void named_bar_sync(int id, int n);
+inline void named_bar_arrive(int id, int n);
+// mbarrier in 8 bytes of shared memory: word 0 = (expected << 16) | pending arrivals, word 1 = phase parity
+inline void mbar_init(void *p, int count)
+{
+  auto *w = static_cast<uint32_t *>(p);
+  __atomic_store_n(w, ((uint32_t)count << 16) | (uint32_t)count, __ATOMIC_SEQ_CST);
+  __atomic_store_n(w + 1, 0u, __ATOMIC_SEQ_CST);
+}
+inline void mbar_arrive(void *p)
+{
+  auto *w = static_cast<uint32_t *>(p);
+  const uint32_t old = __atomic_fetch_sub(w, 1u, __ATOMIC_SEQ_CST);
+  if ((old & 0xFFFFu) == 1u) {   // last arrival: re-arm, then flip the phase (release)
+    __atomic_store_n(w, (old & 0xFFFF0000u) | (old >> 16), __ATOMIC_SEQ_CST);
+    __atomic_fetch_xor(w + 1, 1u, __ATOMIC_SEQ_CST);
+  }
+}
+inline void mbar_wait(void *p, unsigned parity)
+{
+  auto *w = static_cast<uint32_t *>(p);
+  while (__atomic_load_n(w + 1, __ATOMIC_SEQ_CST) == parity) std::this_thread::yield();
+}
 }// namespace emu
 
 #define threadIdx (emu::tls.tid)
@@ -143,6 +189,8 @@ inline void emu::grid_sync()
   if (tls.tid.x == 0 && tls.tid.y == 0 && tls.tid.z == 0) tls.blk->grid->bar.arrive_and_wait();
   __syncthreads();
 }
+inline void emu::named_bar_sync(int id, int n) { tls.blk->named[id].arrive(n, true); }
+inline void emu::named_bar_arrive(int id, int n) { tls.blk->named[id].arrive(n, false); }
 static inline char *emu_dyn_smem()
 {
   auto p = reinterpret_cast<uintptr_t>(emu::tls.blk->smem.data());

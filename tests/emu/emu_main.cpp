@@ -9,7 +9,6 @@
 #include "../../cudacam_b200/csrc/k_hysteresis_uf.cuh"
 #include "../../cudacam_b200/csrc/k_stencil_tile.cuh"
 #ifdef B2C_EMU_FUSED
-#include "../../cudacam_b200/csrc/k_stencil_fused.cuh"
 #include "../../cudacam_b200/csrc/k_stencil_march.cuh"
 #endif
 
@@ -26,7 +25,7 @@ static void fill_gk(float gk[25])
 static int g_emu_channels = 3;
 extern "C" {
 __attribute__((visibility("default"))) void emu_set_channels(int ch) { g_emu_channels = ch; }
-// impl: 1 = tile kernel (EMIT when any stage pointer is given), 0 = fused CTA-tile kernel, 100 + rb = marching kernel with rb rows per band
+// impl: 1 = tile kernel (EMIT when any stage pointer is given), 100 + rb = marching kernel with rb rows per band
 __attribute__((visibility("default"))) int emu_stencil(int impl, const uint8_t *bgr, long long row_stride, long long frame_stride, int w, int h, int y0, int h_glob, int nframes,
                                                        unsigned lo, unsigned hi, uint32_t *map2, uint8_t *mono, uint8_t *blur, float *grad, uint8_t *nms, uint8_t *thresh)
 {
@@ -39,13 +38,7 @@ __attribute__((visibility("default"))) int emu_stencil(int impl, const uint8_t *
   p.map2 = map2; p.map_pitch = (w + 15) / 16; p.map_frame_stride = (long long)h * p.map_pitch;
   p.lo = lo; p.hi = hi;
   fill_gk(p.gk);
-  for (int k = 0; k < 3; ++k) {
-    const float a = (float)(256 * k + lo + 1), b = (float)(256 * k + hi + 1);
-    p.n_lo[k] = ldexpf(4.0f * a * a, -48);
-    p.n_hi[k] = ldexpf(4.0f * b * b, -48);   // fused kernel: sums carry the fp16-subnormal scale 2^-24
-  }
-  p.n_wrap[0] = ldexpf(262144.0f, -48);
-  p.n_wrap[1] = ldexpf(1048576.0f, -48);
+  b2c_fill_thresholds(p);
   p.mono = mono; p.blur = blur; p.grad = grad; p.nms = nms; p.thresh = thresh;
   p.pitch8 = w; p.pitchf = w;
   if (impl == 1) {
@@ -58,8 +51,7 @@ __attribute__((visibility("default"))) int emu_stencil(int impl, const uint8_t *
   }
 #ifdef B2C_EMU_FUSED
   if (impl >= 100) return b2c::march_emu_launch(p, impl - 100);   // impl = 100 + rows per band
-  if (p.channels != 3) return -3;
-  return b2c::fused_emu_launch(p);
+  return -1;
 #else
   return -1;
 #endif

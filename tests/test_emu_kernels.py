@@ -22,24 +22,29 @@ def test_tile_stencil_all_stages(kind, w, h, seed, lo, hi):
     assert np.array_equal(e["map2"][0], O.thresh_to_map2(r["thresh"]))
 
 
-FUSED_CASES = [("scene", 200, 150, 7, 10, 40), ("noise", 96, 61, 8, 10, 40), ("steps", 136, 70, 9, 17, 43), ("scene", 16, 5, 3, 10, 40),
-               ("steps", 480, 130, 2, 3, 200), ("scene", 8, 8, 1, 0, 0), ("noise", 488, 64, 3, 10, 40), ("scene", 720, 64, 3, 10, 40)]
+MARCH_CASES = [("scene", 200, 150, 7, 10, 40), ("noise", 96, 61, 8, 10, 40), ("steps", 136, 70, 9, 17, 43), ("scene", 16, 5, 3, 10, 40),
+               ("steps", 480, 130, 2, 3, 200), ("scene", 8, 8, 1, 0, 0), ("noise", 488, 64, 3, 10, 40), ("scene", 720, 64, 3, 10, 40),
+               # widths that are not a multiple of 8: the last lane of the strip is only partly inside the image
+               ("scene", 201, 50, 7, 10, 40), ("noise", 97, 61, 8, 10, 40), ("steps", 243, 40, 9, 17, 43), ("scene", 13, 9, 3, 10, 40), ("noise", 487, 30, 3, 10, 40)]
 
 
-@pytest.mark.parametrize("impl", [0, 116, 136], ids=["fused", "march16", "march36"])
-@pytest.mark.parametrize("kind,w,h,seed,lo,hi", FUSED_CASES)
-def test_fused_stencil_map(kind, w, h, seed, lo, hi, impl):
-    """impl 0 = fused CTA-tile kernel, 100 + rb = marching warp-per-strip kernel with rb rows per band."""
+def _padded(f, ch=3, top=4):
+    """Rows padded the way the host driver pads them: whole 8-pixel lanes backed by memory, 16-byte aligned."""
+    h, w = f.shape[:2]
+    stride = ((w + 7) // 8 * 8 * ch + 15) // 16 * 16
+    buf = np.zeros((h + 2 * top, stride), np.uint8)
+    buf[top:top + h, :w * ch] = f.reshape(h, w * ch)
+    return buf
+
+
+@pytest.mark.parametrize("rb", [8, 20, 44], ids=["rb8", "rb20", "rb44"])
+@pytest.mark.parametrize("kind,w,h,seed,lo,hi", MARCH_CASES)
+def test_march_stencil_map(kind, w, h, seed, lo, hi, rb):
+    """impl 100 + rb = marching two-warp pipeline kernel with rb rows per band."""
     f = synth.frame(kind, seed, w, h)
     r = O.canny(f, lo, hi, want_edges=False)
-    # these kernels want 16-byte aligned rows: give them a padded copy like the host driver does
-    stride = (w * 3 + 15) // 16 * 16
-    buf = np.zeros((h + 8, stride), np.uint8)
-    buf[4:4 + h, :w * 3] = f.reshape(h, w * 3)
-    e = E.stencil_raw(buf, 4, w, h, lo, hi, impl=impl)
-    if e is None:
-        pytest.skip("fused kernel not in the emulator build")
-    assert np.array_equal(e, O.thresh_to_map2(r["thresh"]))
+    e = E.stencil_raw(_padded(f), 4, w, h, lo, hi, impl=100 + rb)
+    assert e is not None and np.array_equal(e, O.thresh_to_map2(r["thresh"]))
 
 
 @pytest.mark.parametrize("tile_rows", [-1, 0, 4], ids=["unionfind4", "unionfind_coop", "tilerounds"])
@@ -89,9 +94,9 @@ def test_band_mode_stencil_equals_whole_image():
     assert np.array_equal(band, whole[y0:y0 + rows])
 
 
-@pytest.mark.parametrize("impl", [0, 126], ids=["fused", "march"])
+@pytest.mark.parametrize("impl", [132], ids=["march"])
 @pytest.mark.parametrize("v", [0, 3, 100, 255])
-def test_fused_flat_picture_takes_dense_replay(v, impl):
+def test_march_flat_picture_takes_dense_replay(v, impl):
     """Flat regions make S % 159 == 0 for every pixel: the work list overflows and the dense replay runs."""
     f = np.full((70, 248, 3), v, np.uint8)
     f[30:40, 100:140] = (v + 60) % 256
@@ -102,8 +107,8 @@ def test_fused_flat_picture_takes_dense_replay(v, impl):
     assert e is not None and np.array_equal(e, O.thresh_to_map2(r["thresh"]))
 
 
-@pytest.mark.parametrize("impl", [0, 126], ids=["fused", "march"])
-def test_fused_band_mode_equals_whole_image(impl):
+@pytest.mark.parametrize("impl", [120, 132], ids=["march20", "march32"])
+def test_march_band_mode_equals_whole_image(impl):
     w, h = 248, 150
     f = synth.frame("scene", 23, w, h)
     whole = O.thresh_to_map2(O.canny(f, want_edges=False)["thresh"])
@@ -166,15 +171,22 @@ def test_hysteresis_unionfind4_diagonal_staircase_across_tiles():
     assert np.array_equal(edges[0], O.hysteresis(t))
 
 
-@pytest.mark.parametrize("w,h,rb", [(8, 3, 16), (240, 36, 36), (248, 37, 26), (480, 12, 6), (1000, 23, 16)])
+@pytest.mark.parametrize("w,h,rb", [(8, 3, 16), (240, 36, 36), (248, 37, 26), (480, 12, 6), (1000, 23, 16), (241, 25, 8), (239, 13, 20), (249, 50, 44), (9, 1, 8)])
 def test_march_geometry_corner_cases(w, h, rb):
-    """Strip / band boundaries of the marching kernel: widths around multiples of 240, heights around the block size."""
+    """Strip / band boundaries of the marching kernel: widths around multiples of 240 and 8, heights around the block size."""
     f = synth.frame("scene", 40 + w, w, h)
     r = O.canny(f, 10, 40, want_edges=False)
-    stride = (w * 3 + 15) // 16 * 16
-    buf = np.zeros((h + 8, stride), np.uint8)
-    buf[4:4 + h, :w * 3] = f.reshape(h, w * 3)
-    e = E.stencil_raw(buf, 4, w, h, 10, 40, impl=100 + rb)
+    e = E.stencil_raw(_padded(f), 4, w, h, 10, 40, impl=100 + rb)
+    assert e is not None and np.array_equal(e, O.thresh_to_map2(r["thresh"]))
+
+
+def test_march_long_band_many_blocks():
+    """One band of many 12-row blocks: the producer / consumer hand-over of the blur ring is exercised dozens of times,
+    on noise (every lane busy in the sparse stages) so that the two warps drift against each other."""
+    w, h = 248, 300
+    f = synth.frame("noise", 77, w, h)
+    r = O.canny(f, 10, 40, want_edges=False)
+    e = E.stencil_raw(_padded(f), 4, w, h, 10, 40, impl=100 + 296)
     assert e is not None and np.array_equal(e, O.thresh_to_map2(r["thresh"]))
 
 
@@ -199,8 +211,5 @@ def test_other_input_formats(kind, w, h, seed, ch):
     e = E.stencil(g, impl=1, stages=True)
     for k in ("mono", "blur", "nms", "thresh"):
         assert np.array_equal(e[k], r[k]), k
-    stride = (w * ch + 15) // 16 * 16
-    buf = np.zeros((h + 8, stride), np.uint8)
-    buf[4:4 + h, :w * ch] = g.reshape(h, w * ch)
-    m = E.stencil_raw(buf, 4, w, h, impl=126, channels=ch)
+    m = E.stencil_raw(_padded(g, ch), 4, w, h, impl=126, channels=ch)
     assert m is not None and np.array_equal(m, O.thresh_to_map2(r["thresh"]))

@@ -28,13 +28,14 @@ def _check_all(c, f, r):
     assert np.array_equal(c.thresh(), r["thresh"])
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2], ids=["march", "tile", "fused"])
+@pytest.mark.parametrize("impl", [0, 1], ids=["march", "tile"])
 @pytest.mark.parametrize("kind,w,h,seed,lo,hi", [
     ("scene", 1280, 720, 0xC0FFEE, 10, 40),      # BASELINE config 1
     ("scene", 1280, 720, 0xC0FFEE, 17, 43),      # thresholds of the reference's screenshot
     ("noise", 641, 363, 2, 10, 40), ("steps", 800, 600, 3, 10, 40), ("steps", 333, 222, 4, 3, 200),
     ("scene", 31, 33, 6, 10, 40), ("noise", 1, 1, 1, 10, 40), ("scene", 16, 1, 2, 10, 40), ("scene", 5, 300, 2, 10, 40),
     ("scene", 1920, 1080, 5, 10, 40), ("steps", 1920, 1080, 8, 10, 40), ("noise", 1000, 700, 8, 17, 43), ("scene", 248, 2000, 4, 10, 40),
+    ("scene", 1283, 721, 9, 10, 40), ("noise", 250, 129, 3, 10, 40), ("scene", 3840, 2160, 11, 10, 40),
 ])
 def test_frame_vs_oracle(impl, kind, w, h, seed, lo, hi):
     f = synth.frame(kind, seed, w, h)
