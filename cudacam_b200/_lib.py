@@ -34,6 +34,7 @@ _SIGS = {
     "b2c_run_device": (_i, [_vp, _u8p, _sz, _sz, _i, _u8p, _sz, _sz, _vp]),
     "b2c_stencil_device": (_i, [_vp, _u8p, _sz, _sz, _i, _vp]),
     "b2c_hysteresis_device": (_i, [_vp, _i, _u8p, _sz, _sz, _vp]),
+    "b2c_load_thresh": (_i, [_vp, _vp, _sz]),
     "b2c_run_batch_host": (_i, [_vp, _u8p, _sz, _i, _u8p, _i]),
     "b2c_get_buffer": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_sz), C.POINTER(_i)]),
     "b2c_download": (_i, [_vp, _i, _vp, _sz]),
@@ -47,15 +48,17 @@ _SIGS = {
     "b2c_stream": (_vp, [_vp]),
     "b2c_create_band": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i]),
     "b2c_band_stencil": (_i, [_vp, _u8p, _sz, _vp]),
-    "b2c_band_hysteresis": (_i, [_vp, _i, _i, C.POINTER(_i), _vp]),
-    "b2c_band_boundary_ptr": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_i)]),
-    "b2c_band_ghost_ptr": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_i)]),
-    "b2c_band_flag_ptr": (_i, [_vp, C.POINTER(_vp)]),
+    "b2c_band_hysteresis": (_i, [_vp, _vp]),
+    "b2c_band_seam_bytes": (_i, [_vp, C.POINTER(_sz)]),
+    "b2c_band_seam_publish": (_i, [_vp, C.POINTER(_vp), _vp]),
+    "b2c_band_seam_solve": (_i, [_vp, _vp, _i, _i, _vp]),
+    "b2c_band_status": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
+    "b2c_band_input": (_i, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
     "b2c_band_p2p_export": (_i, [_vp, _vp]),
     "b2c_band_p2p_open": (_i, [_vp, _vp, _i, _i]),
-    "b2c_band_p2p_converge": (_i, [_vp, _i, C.POINTER(_i), _vp]),
-    "b2c_band_input": (_i, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
-    "b2c_band_p2p_halo": (_i, [_vp, _vp]),
+    "b2c_band_p2p_open_local": (_i, [_vp, C.POINTER(_vp), _i, _i]),
+    "b2c_band_p2p_halo": (_i, [_vp, _vp, _i]),
+    "b2c_band_p2p_seam": (_i, [_vp, _vp, _i]),
     "b2c_strerror": (C.c_char_p, [_i]),
     "b2c_last_cuda_error": (C.c_char_p, [_vp]),
     "b2c_version": (C.c_char_p, []),

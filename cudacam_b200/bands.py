@@ -2,14 +2,17 @@
 
 No reference counterpart: the reference is single-GPU.  Each rank owns a contiguous band of rows.
 The fused stencil needs 4 rows of INPUT beyond each interior seam (2 Gaussian + 1 Sobel + 1 NMS), exchanged once with
-the neighbours (NCCL send/recv over NVLink on GPUs); the reference's zero padding applies only at the true image
-border.  Hysteresis: every rank resolves its band on the device (union-find kernel), then the first/last row of its
-edge bit-plane goes to the neighbours' ghost rows; ranks whose ghost rows gained bits re-resolve with those rows as
-extra seeds; the loop ends when an all-reduce (MAX) of "my ghost rows changed" is 0.  The result is bit-identical to
-the unsharded run because both compute the same fixpoint.
+the neighbours; the reference's zero padding applies only at the true image border.  Hysteresis: every rank resolves
+its band on the device (union-find kernels) and keeps planes and forest; then ONE exchange: every rank publishes its
+seam record (edge / unresolved-weak bit rows of its first and last row + a component label per unresolved run), the
+records are all-gathered, and every rank solves the same small connected-components problem over all seams and
+promotes its own components that reach an edge pixel of any band.  The result is bit-identical to the unsharded run
+because both compute the same fixpoint.
 
-torch.distributed is plumbing here (rendezvous, send/recv, all_reduce); all pixel work is behind `backend`:
-`CudaBandBackend` (the C ABI of libb200canny.so) on GPUs, and an emulator-based stand-in in tests (gloo, CPU).
+Transports: peer memory (ranks of one box: halo rows and records are plain stores into the peers' mapped buffers) or
+torch.distributed collectives (NCCL on GPUs, gloo in the CPU tests).  torch.distributed is plumbing here; all pixel
+work is behind `backend`: `CudaBandBackend` (the C ABI of libb200canny.so) on GPUs, an emulator-based stand-in in
+tests.  The C++ twin of this driver is b2c::BandRunner (include/b200canny.hpp).
 """
 import ctypes as C
 
@@ -53,8 +56,12 @@ class CudaBandBackend:
         self.row_stride = st.value
         with torch.cuda.device(device):
             self.buf = torch.as_tensor(_DevArray(p.value, (rows + 2 * HALO, self.row_stride), "|u1"), device=f"cuda:{device}")
-        self.wpr = (width + 31) // 32
-        self._views = {}
+        n = C.c_size_t()
+        _lib.check(_lib.lib.b2c_band_seam_bytes(h, C.byref(n)), h, "b2c_band_seam_bytes")
+        self.seam_bytes = n.value
+        self.p2p = False
+        self.own_stream = False   # launch on the handle's own stream instead of torch's current one (see open_local)
+        self._all = None
 
     def close(self):
         if self._h:
@@ -64,6 +71,8 @@ class CudaBandBackend:
     def _stream(self):
         # torch's current stream on this band's device; handle 0 is the legacy default stream, which the C ABI
         # spells cudaStreamLegacy (0x1) because 0 means "the handle's own stream" there
+        if self.own_stream:
+            return None
         return self.torch.cuda.current_stream(self.device).cuda_stream or 1
 
     def input_rows(self, r0, r1):
@@ -75,18 +84,38 @@ class CudaBandBackend:
         t = self.torch.from_numpy(np.ascontiguousarray(band_host).reshape(self.rows, self.width * 3))
         self.buf[HALO:HALO + self.rows, :self.width * 3].copy_(t, non_blocking=False)
 
+    def load_thresh(self, thresh_host):
+        """(rows, w) uint8 map of 0 / 128 / 255 in place of a stencil run (hysteresis on maps produced elsewhere)."""
+        t = np.ascontiguousarray(thresh_host, np.uint8)
+        assert t.shape == (self.rows, self.width)
+        _lib.check(_lib.lib.b2c_load_thresh(self._h, t.ctypes.data, t.strides[0]), self._h, "b2c_load_thresh")
+
     def stencil(self):
         ptr = self.buf.data_ptr() + HALO * self.row_stride
         _lib.check(_lib.lib.b2c_band_stencil(self._h, ptr, self.row_stride, self._stream()), self._h, "b2c_band_stencil")
 
-    def hysteresis(self, first, write_edges):
-        """write_edges: False = bit plane only, True = also the u8 map, "only" = just expand the final bit plane."""
-        we = 2 if write_edges == "only" else 1 if write_edges else 0
-        _lib.check(_lib.lib.b2c_band_hysteresis(self._h, 1 if first else 0, we, None, self._stream()), self._h, "b2c_band_hysteresis")
+    def hysteresis(self):
+        """Band-local fixpoint (planes and forest are kept for the seam solve); writes the u8 edge map."""
+        _lib.check(_lib.lib.b2c_band_hysteresis(self._h, self._stream()), self._h, "b2c_band_hysteresis")
 
+    # -- cross-band hysteresis: collective transport -------------------------------------------------------------
+    def seam_record(self):
+        """Publishes this band's seam record; returns it as a uint8 device tensor (owned by the handle)."""
+        p = C.c_void_p()
+        _lib.check(_lib.lib.b2c_band_seam_publish(self._h, C.byref(p), self._stream()), self._h, "b2c_band_seam_publish")
+        return self.torch.as_tensor(_DevArray(p.value, self.seam_bytes, "|u1"), device=f"cuda:{self.device}")
+
+    def gather_buffer(self, world):
+        if self._all is None or self._all.numel() != world * self.seam_bytes:
+            self._all = self.torch.empty(world * self.seam_bytes, dtype=self.torch.uint8, device=f"cuda:{self.device}")
+        return self._all
+
+    def seam_solve(self, all_records, world, rank):
+        _lib.check(_lib.lib.b2c_band_seam_solve(self._h, all_records.data_ptr(), world, rank, self._stream()), self._h, "b2c_band_seam_solve")
+
+    # -- cross-band hysteresis and input halo: peer memory -------------------------------------------------------
     def enable_p2p(self, dist, rank, world, group=None):
-        """Maps the other ranks' mailboxes (CUDA IPC) so that the cross-band rounds run on the devices (NVLink peer
-        stores, device-side convergence) instead of through NCCL + host.  Ranks must be on one box."""
+        """Maps the other ranks' mailboxes and input buffers (CUDA IPC).  Ranks must be on one box."""
         h = (C.c_ubyte * 144)()
         _lib.check(_lib.lib.b2c_band_p2p_export(self._h, h), self._h, "b2c_band_p2p_export")
         mine = self.torch.tensor(list(h), dtype=self.torch.uint8, device=f"cuda:{self.device}")
@@ -96,38 +125,18 @@ class CudaBandBackend:
         _lib.check(_lib.lib.b2c_band_p2p_open(self._h, buf, world, rank), self._h, "b2c_band_p2p_open")
         self.p2p = True
 
-    def halo_p2p(self):
-        _lib.check(_lib.lib.b2c_band_p2p_halo(self._h, self._stream()), self._h, "b2c_band_p2p_halo")
+    def halo_p2p(self, phase=0):
+        """phase: 0 = push + wait (one band per process), 1 = push, 2 = wait (see run_local)."""
+        _lib.check(_lib.lib.b2c_band_p2p_halo(self._h, self._stream(), phase), self._h, "b2c_band_p2p_halo")
 
-    def converge(self, rounds_per_sync=16):
-        n = C.c_int(0)
-        _lib.check(_lib.lib.b2c_band_p2p_converge(self._h, rounds_per_sync, C.byref(n), self._stream()), self._h, "b2c_band_p2p_converge")
-        return n.value
+    def seam_p2p(self, phase=0):
+        _lib.check(_lib.lib.b2c_band_p2p_seam(self._h, self._stream(), phase), self._h, "b2c_band_p2p_seam")
 
-    def seeded(self):
-        """int32[1] device tensor: 1 if the last re-entry call found a ghost pixel that seeded something new."""
-        if "flag" not in self._views:
-            p = C.c_void_p()
-            _lib.check(_lib.lib.b2c_band_flag_ptr(self._h, C.byref(p)), self._h, "flag")
-            self._views["flag"] = self.torch.as_tensor(_DevArray(p.value, 1, "<i4"), device=f"cuda:{self.device}")
-        return self._views["flag"]
-
-    def _view(self, kind, which):
-        key = (kind, which)
-        if key not in self._views:
-            p, n = C.c_void_p(), C.c_int()
-            f = _lib.lib.b2c_band_boundary_ptr if kind == "boundary" else _lib.lib.b2c_band_ghost_ptr
-            _lib.check(f(self._h, which, C.byref(p), C.byref(n)), self._h, kind)
-            self._views[key] = self.torch.as_tensor(_DevArray(p.value, n.value, "<i4"), device=f"cuda:{self.device}")
-        return self._views[key]
-
-    def boundary(self, which):
-        """int32 tensor view of the first (0) / last (1) row of the edge bit-plane."""
-        return self._view("boundary", which)
-
-    def ghost(self, which):
-        """int32 tensor view of the ghost row above (0) / below (1) the band."""
-        return self._view("ghost", which)
+    def status(self):
+        """(weak runs promoted by the last solve, peer time-out flag) -- blocking."""
+        n, e = C.c_int(0), C.c_int(0)
+        _lib.check(_lib.lib.b2c_band_status(self._h, C.byref(n), C.byref(e)), self._h, "b2c_band_status")
+        return n.value, e.value
 
     def sync(self):
         self.torch.cuda.synchronize(self.device)
@@ -144,18 +153,27 @@ class CudaBandBackend:
         return out
 
 
+def open_local(backends):
+    """Peer wiring for CudaBandBackends that live in ONE process (one or several devices): every band gets the others'
+    mailboxes and input buffers as plain pointers.  The bands then launch on their handles' OWN streams: the peer-to-
+    peer kernels wait on the device for the other bands' stores, which on one shared stream would never be issued."""
+    n = len(backends)
+    arr = (C.c_void_p * n)(*[b._h for b in backends])
+    for r, b in enumerate(backends):
+        _lib.check(_lib.lib.b2c_band_p2p_open_local(b._h, arr, n, r), b._h, "b2c_band_p2p_open_local")
+        b.p2p = True
+        b.own_stream = True
+
+
 class BandCanny:
-    """Drives one rank's band: halo exchange, stencil, cross-band hysteresis to the global fixpoint."""
+    """Drives one rank's band: halo exchange, stencil, band-local hysteresis, one seam exchange."""
 
     def __init__(self, backend, rank, world, dist=None, group=None):
         self.b, self.rank, self.world, self.dist, self.group = backend, rank, world, dist, group
-        self.rounds = 0
+        self.exchanges = 0
 
-    # -- plumbing ------------------------------------------------------------------------------------------------
     def _exchange(self, send_up, recv_up, send_down, recv_down):
         """send_up goes to rank-1 (lands in its recv_down), send_down to rank+1 (its recv_up)."""
-        if self.world == 1:
-            return
         d = self.dist
         ops = []
         if self.rank > 0:
@@ -167,75 +185,73 @@ class BandCanny:
 
     def exchange_input_halos(self):
         b, n = self.b, self.b.rows
-        if self.world > 1 and getattr(b, "p2p", False):
+        if self.world == 1:
+            return
+        if getattr(b, "p2p", False):
             b.halo_p2p()   # peer stores into the neighbours' buffers + device-side arrival counters
             return
-        # contiguous staging: rows of a strided buffer are contiguous blocks already (full-stride rows)
         self._exchange(b.input_rows(HALO, 2 * HALO), b.input_rows(0, HALO), b.input_rows(n, n + HALO), b.input_rows(n + HALO, n + 2 * HALO))
 
     def run(self):
-        """Stencil + hysteresis of this band; returns the number of global hysteresis rounds used."""
-        b, d = self.b, self.dist
-        b.ghost(0).zero_()   # ghost rows = the image border's zero padding until a neighbour says otherwise
-        b.ghost(1).zero_()
+        """Stencil + hysteresis of this band; returns the number of cross-band exchanges (0 or 1)."""
+        b = self.b
         self.exchange_input_halos()
         b.stencil()
-        # band-local fixpoint (planes + union-find forest are kept).  Every resolve pass also writes the u8 edge map,
-        # so there is no separate expansion pass once the rounds have converged.
-        b.hysteresis(True, write_edges=True)
-        rounds = 1
-        if self.world > 1 and getattr(b, "p2p", False):
-            rounds = max(1, b.converge() - 1)   # device-side rounds over NVLink peer memory (the last one finds nothing new)
-        while self.world > 1 and not getattr(b, "p2p", False):
-            # boundary rows of the edge bit-plane -> the neighbours' ghost rows; re-entry seeds the weak runs that
-            # touch a strong ghost pixel and resolves their components; stop when no rank was seeded anything new.
-            # (One all_gather of rows + flag per round instead of send/recv + all_reduce was measured SLOWER: the
-            # extra small tensor ops on the host cost more than the second NCCL launch.)
-            self._exchange(b.boundary(0), b.ghost(0), b.boundary(1), b.ghost(1))
-            b.hysteresis(False, write_edges=True)
-            flag = b.seeded().clone()
-            d.all_reduce(flag, op=d.ReduceOp.MAX, group=self.group)
-            if int(flag.item()) == 0:
-                break
-            rounds += 1
-        self.rounds = rounds
-        return rounds
+        b.hysteresis()
+        self.exchanges = 0
+        if self.world > 1:
+            if getattr(b, "p2p", False):
+                b.seam_p2p()
+            else:
+                rec = b.seam_record()
+                allr = b.gather_buffer(self.world)
+                self.dist.all_gather_into_tensor(allr, rec, group=self.group)
+                b.seam_solve(allr, self.world, self.rank)
+            self.exchanges = 1
+        return self.exchanges
 
 
-def run_local(backends):
-    """All bands driven from ONE process (bands on the same or on different GPUs; copies between devices go over
-    NVLink peer-to-peer).  Same protocol as BandCanny.run without a process group: used for the 1-GPU data point of
-    config 5, for the single-GPU tests of the band logic, and by hosts that prefer one thread for the whole box.
-    Returns the number of global hysteresis rounds."""
+def run_local(backends, stencil=True):
+    """All bands driven from ONE process (bands on the same or on different GPUs).  Same steps as BandCanny.run without
+    a process group: with peer wiring (open_local) the halo rows and seam records travel through the peer-to-peer
+    kernels; otherwise by tensor copies.  stencil=False: hysteresis only, on maps loaded with load_thresh.  Returns the
+    number of cross-band exchanges."""
     n = len(backends)
+    p2p = n > 1 and all(getattr(b, "p2p", False) for b in backends)
     for b in backends:
-        b.ghost(0).zero_()
-        b.ghost(1).zero_()
-    for i in range(n - 1):
-        up, dn = backends[i], backends[i + 1]
-        dn.input_rows(0, HALO).copy_(up.input_rows(up.rows, up.rows + HALO), non_blocking=True)
-        up.input_rows(up.rows + HALO, up.rows + 2 * HALO).copy_(dn.input_rows(HALO, 2 * HALO), non_blocking=True)
+        b.sync()   # the uploads ran on other streams than the bands' own
+    if stencil:
+        if p2p:   # every push is issued before the first wait
+            for b in backends:
+                b.halo_p2p(1)
+            for b in backends:
+                b.halo_p2p(2)
+        else:
+            for i in range(n - 1):
+                up, dn = backends[i], backends[i + 1]
+                dn.input_rows(0, HALO).copy_(up.input_rows(up.rows, up.rows + HALO), non_blocking=True)
+                up.input_rows(up.rows + HALO, up.rows + 2 * HALO).copy_(dn.input_rows(HALO, 2 * HALO), non_blocking=True)
+            for b in backends:
+                b.sync()
+        for b in backends:
+            b.stencil()
+    for b in backends:
+        b.hysteresis()
+    if n > 1:
+        if p2p:
+            for b in backends:
+                b.seam_p2p(1)
+            for b in backends:
+                b.seam_p2p(2)
+        else:
+            recs = [b.seam_record() for b in backends]
+            for b in backends:
+                b.sync()
+            for r, b in enumerate(backends):
+                allr = b.gather_buffer(n)
+                for k, rec in enumerate(recs):
+                    allr[k * b.seam_bytes:(k + 1) * b.seam_bytes].copy_(rec)
+                b.seam_solve(allr, n, r)
     for b in backends:
         b.sync()
-    for b in backends:
-        b.stencil()
-    for b in backends:
-        b.hysteresis(True, write_edges=True)
-    rounds = 1
-    while n > 1:
-        for b in backends:
-            b.sync()
-        for i in range(n - 1):
-            up, dn = backends[i], backends[i + 1]
-            dn.ghost(0).copy_(up.boundary(1))
-            up.ghost(1).copy_(dn.boundary(0))
-        for b in backends:
-            b.sync()
-        for b in backends:
-            b.hysteresis(False, write_edges=True)
-        if not any(bool(b.seeded().item()) for b in backends):
-            break
-        rounds += 1
-    for b in backends:
-        b.sync()
-    return rounds
+    return 1 if n > 1 else 0

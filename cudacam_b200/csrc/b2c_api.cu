@@ -19,12 +19,13 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/b200canny.h"
 #include "b2c_device.cuh"
-#include "k_hysteresis.cuh"
 #include "k_hysteresis_uf.cuh"
 #include "k_band_p2p.cuh"
+#include "k_band_seam.cuh"
 #include "k_stencil_march.cuh"
 #include "k_stencil_tile.cuh"
 #include "k_views.cuh"
@@ -48,10 +49,7 @@ struct b2c_ctx {
   int march_rb = 0;           // rows per band of the marching kernel, 0 = automatic
   int march_ctas_per_sm = 0;  // resident CTAs per SM of the marching kernel (occupancy query at creation)
   int march_extra_smem = 0;   // profiling knob: extra dynamic shared memory per CTA (lowers the occupancy)
-  int hyst_impl = 0;          // 0 union-find as 3 launches (tile, border, resolve), 1 tile rounds (cooperative), 2 union-find as one cooperative launch
-  int hyst_tile_rows = 16;
   int uf_spread = 1;
-  int hyst_max_rounds = 1 << 20;
 
   // geometry
   int map_pitch = 0;      // u32 per row of the 2-bit map
@@ -64,8 +62,8 @@ struct b2c_ctx {
 
   // device memory
   uint8_t *d_in = nullptr;
-  uint32_t *d_map2 = nullptr;
-  uint32_t *d_S_base = nullptr, *d_C_base = nullptr;   // incl. ghost rows
+  uint32_t *d_map2 = nullptr;   // 2-bit map view of the planes (accessor format, made on demand)
+  uint32_t *d_S_base = nullptr, *d_C_base = nullptr, *d_E_base = nullptr;   // bit planes incl. one zero ghost row above and below each frame
   uint8_t *d_edges = nullptr;
   uint8_t *d_mono = nullptr, *d_blur = nullptr, *d_nms = nullptr, *d_thresh = nullptr, *d_view = nullptr;
   float *d_grad = nullptr;
@@ -75,13 +73,12 @@ struct b2c_ctx {
   int *d_bcount = nullptr;       // their lengths (zeroed again by the resolve kernel)
   int bcap = 0;                  // entries per frame
   uint8_t *d_zeros = nullptr;
-  int uf_grid = 0;
   int *h_flags = nullptr;   // pinned mirror
 
   // last input (for on-demand stage buffers)
   const uint8_t *last_in = nullptr;
   size_t last_row_stride = 0;
-  bool have_frame = false, stages_valid = false;
+  bool have_frame = false, stages_valid = false, edges_valid = false, map2_valid = false;
   int last_stage = -1;
 
   // host pipeline
@@ -98,17 +95,19 @@ struct b2c_ctx {
   // band mode
   bool band = false;
   int band_y0 = 0, h_glob = 0;
-  // band mode, peer-to-peer rounds: own mailbox + control ints, the other ranks' mailboxes mapped through CUDA IPC
+  // band mode: seam records (k_band_seam.cuh); peer-to-peer: own mailbox, the other ranks' mailboxes mapped through CUDA IPC
+  uint32_t *d_seam_rec = nullptr;          // own record (NCCL / gloo all-gather path)
+  int *d_seam_roots = nullptr, *d_seam_hkey = nullptr, *d_seam_hval = nullptr, *d_seam_P = nullptr, *d_seam_pre = nullptr;
+  int *d_seam_ctl = nullptr, *h_seam_ctl = nullptr;
+  int seam_run = 0;
   uint32_t *d_mailbox = nullptr;
-  int *d_p2pctl = nullptr;
-  int *h_p2pctl = nullptr;
   void *peer_mail[b2c::BP_MAXW] = {};
   void *peer_in[2] = { nullptr, nullptr };   // band input buffers of the upper / lower neighbour
+  bool peers_ipc = false;                  // peer pointers came from cudaIpcOpenMemHandle (to be closed)
   int peer_rows_up = 0;
   uint8_t *d_band_in = nullptr;            // own band input buffer: 4 halo rows, the band, 4 halo rows
   int p2p_world = 0, p2p_rank = 0, p2p_run = 0;
 
-  int hyst_grid = 0, hyst_smem = 0;
   long long launches = 0;
   std::string last_err;
 };
@@ -146,6 +145,7 @@ void fill_gk(float gk[25])
 
 uint32_t *S0(b2c_ctx *c) { return c->d_S_base + c->plane_pitch; }
 uint32_t *C0(b2c_ctx *c) { return c->d_C_base + c->plane_pitch; }
+uint32_t *E0(b2c_ctx *c) { return c->d_E_base + c->plane_pitch; }
 long long plane_frame_stride(const b2c_ctx *c) { return (long long)(c->rows_alloc + 2) * c->plane_pitch; }
 
 int alloc_common(b2c_ctx *c)
@@ -161,16 +161,17 @@ int alloc_common(b2c_ctx *c)
   cudaDeviceProp prop;
   CK(c, cudaGetDeviceProperties(&prop, c->dev));
   c->sm_count = prop.multiProcessorCount;
-  if (!prop.cooperativeLaunch) {
-    c->last_err = "device does not support cooperative launch";
+  if (c->wpr >= (1 << b2c::UF_XW_BITS) || rows >= (1 << (32 - b2c::UF_XW_BITS)) || (long long)rows * c->plane_pitch * 32 >= (1ll << 31)) {
+    c->last_err = "image or band too large for 32-bit union-find node ids / border-list entries";   // (split it into more row bands)
     return B2C_ERR_UNSUPPORTED;
   }
-  CK(c, cudaMalloc(&c->d_map2, (size_t)nb * rows * c->map_pitch * 4));
   const size_t plane_bytes = (size_t)nb * plane_frame_stride(c) * 4;
   CK(c, cudaMalloc(&c->d_S_base, plane_bytes));
   CK(c, cudaMalloc(&c->d_C_base, plane_bytes));
+  CK(c, cudaMalloc(&c->d_E_base, plane_bytes));
   CK(c, cudaMemset(c->d_S_base, 0, plane_bytes));
   CK(c, cudaMemset(c->d_C_base, 0, plane_bytes));
+  CK(c, cudaMemset(c->d_E_base, 0, plane_bytes));
   CK(c, cudaMalloc(&c->d_edges, (size_t)nb * c->edges_frame_stride));
   CK(c, cudaMalloc(&c->d_parent, (size_t)nb * rows * c->plane_pitch * 32 * sizeof(int)));
   {
@@ -196,22 +197,6 @@ int alloc_common(b2c_ctx *c)
   }
   for (auto &e : c->ev_t) CK(c, cudaEventCreate(&e));
 
-  // launch geometry of the two cooperative hysteresis variants (options hyst_impl 1 / 2): as many CTAs as fit
-  c->hyst_smem = b2c::hyst_smem_bytes(c->hyst_tile_rows);
-  CK(c, cudaFuncSetAttribute(b2c::k_hysteresis, cudaFuncAttributeMaxDynamicSharedMemorySize, c->hyst_smem));
-  int per_sm = 0;
-  CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b2c::k_hysteresis, b2c::HYST_THREADS, c->hyst_smem));
-  if (per_sm < 1) {
-    c->last_err = "hysteresis kernel does not fit on an SM";
-    return B2C_ERR_CUDA;
-  }
-  c->hyst_grid = c->sm_count * std::min(per_sm, 4);
-  CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b2c::k_hysteresis_uf, b2c::UF_THREADS, b2c::UF_SMEM));
-  if (per_sm < 1) {
-    c->last_err = "union-find hysteresis kernel does not fit on an SM";
-    return B2C_ERR_CUDA;
-  }
-  c->uf_grid = c->sm_count * per_sm;
   CK(c, cudaFuncSetAttribute(b2c::k_uf_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, b2c::UT_SMEM));
   CK(c, cudaFuncSetAttribute(b2c::k_stencil_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2c::TILE_SMEM));
   CK(c, cudaFuncSetAttribute(b2c::k_stencil_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2c::TILE_SMEM));
@@ -232,9 +217,10 @@ void fill_stencil_params(b2c_ctx *c, B2cStencilParams &p, const uint8_t *bgr, si
   p.h_glob = c->band ? c->h_glob : c->h;
   p.nframes = n;
   p.channels = c->ch;
-  p.map2 = c->d_map2;
-  p.map_pitch = c->map_pitch;
-  p.map_frame_stride = (long long)c->rows_alloc * c->map_pitch;
+  p.pl_S = reinterpret_cast<uint16_t *>(S0(c));
+  p.pl_C = reinterpret_cast<uint16_t *>(C0(c));
+  p.pl_pitch16 = c->plane_pitch * 2;
+  p.pl_frame_stride16 = plane_frame_stride(c) * 2;
   p.lo = c->lo;
   p.hi = c->hi;
   fill_gk(p.gk);
@@ -257,6 +243,8 @@ int launch_stencil(b2c_ctx *c, const uint8_t *bgr, size_t row_stride, size_t fra
     CK(c, cudaGetLastError());
   }
   c->launches++;
+  c->map2_valid = false;
+  c->edges_valid = false;
   return B2C_OK;
 }
 
@@ -287,15 +275,12 @@ int launch_stencil_emit(b2c_ctx *c, const uint8_t *bgr, size_t row_stride, cudaS
   return B2C_OK;
 }
 
-int launch_hysteresis(b2c_ctx *c, int n, uint8_t *edges, size_t edges_pitch, size_t edges_frame_stride, int skip_init, int skip_expand, cudaStream_t st)
+void fill_hyst_params(b2c_ctx *c, B2cHystParams &p, int n, uint8_t *edges, size_t edges_pitch, size_t edges_frame_stride)
 {
-  B2cHystParams p;
   memset(&p, 0, sizeof(p));
-  p.map2 = c->d_map2;
-  p.map_pitch = c->map_pitch;
-  p.map_frame_stride = (long long)c->rows_alloc * c->map_pitch;
   p.S = S0(c);
   p.C = C0(c);
+  p.E = E0(c);
   p.plane_pitch = c->plane_pitch;
   p.plane_frame_stride = plane_frame_stride(c);
   p.w = c->w;
@@ -305,76 +290,34 @@ int launch_hysteresis(b2c_ctx *c, int n, uint8_t *edges, size_t edges_pitch, siz
   p.edges_pitch = (long long)edges_pitch;
   p.edges_frame_stride = (long long)edges_frame_stride;
   p.flags = c->d_flags;
-  p.max_rounds = c->hyst_max_rounds;
-  p.tile_rows = c->hyst_tile_rows;
-  p.skip_init = skip_init;
-  p.skip_expand = skip_expand;
   p.parent = c->d_parent;
   p.parent_frame_stride = (long long)c->rows_alloc * c->plane_pitch * 32;
   p.spread = c->uf_spread;
-  void *args[] = { &p };
-  if (c->hyst_impl == 0 && c->wpr <= 1024) {   // (list entries hold the word index in 10 bits: wider images take the cooperative kernel)
-    // union-find as three ordinary launches (tile, border, resolve+expand; row-band re-entry: seed, resolve) -- no
-    // barrier inside, no host round trip between
-    const dim3 gt((c->wpr + b2c::UT_WORDS - 1) / b2c::UT_WORDS, (c->rows_alloc + b2c::UT_ROWS - 1) / b2c::UT_ROWS, n);
-    const bool pt = c->hyst_phase_timing;
-    if (pt) cudaEventRecord(c->ev_h[0], st);
-    const int T = b2c::UFK_THREADS;
-    if (skip_init) {   // row-band re-entry: seeds from the ghost rows on the retained forest
-      b2c::k_uf_seed<<<dim3((c->wpr + T - 1) / T, 2, n), T, 0, st>>>(p);
-    } else {
-      b2c::k_uf_tile<<<gt, b2c::UT_THREADS, b2c::UT_SMEM, st>>>(p, c->d_blist, c->d_bcount, c->bcap);
-    }
-    if (pt) cudaEventRecord(c->ev_h[1], st);
-    {
-      // border list: typically ~12 % of bcap entries; a quarter of the worst case in blocks, grid-stride for the rest
-      const int gb = std::max(1, (c->bcap + T - 1) / T);   // 4 threads per entry, a quarter of the worst case in blocks
-      if (!skip_init) {
-        b2c::k_uf_border<<<dim3(gb, 1, n), T, 0, st>>>(p, c->d_blist, c->d_bcount, c->bcap);
-        c->launches++;
-      }
-      if (pt) cudaEventRecord(c->ev_h[2], st);
-      const int tx = c->wpr >= 256 ? 256 : c->wpr > 32 ? 64 : 32, ty = 256 / tx;   // 256 threads = tx words x ty rows
-      const dim3 gr((c->wpr + tx - 1) / tx, (c->rows_alloc + 2 * ty - 1) / (2 * ty), n), br(tx, ty);   // a thread takes 2 rows
-      if (edges && !skip_expand) b2c::k_uf_resolve<true><<<gr, br, 0, st>>>(p, c->d_bcount);
-      else b2c::k_uf_resolve<false><<<gr, br, 0, st>>>(p, c->d_bcount);
-      if (pt) cudaEventRecord(c->ev_h[3], st);
-    }
-    c->launches += 1;   // (+1 at the end of the function: tile / seed and resolve)
-    CK(c, cudaGetLastError());
-  } else if (c->hyst_impl != 1) {
-    // one warp per plane row, at most one full wave of CTAs
-    const long long rows = (long long)n * c->rows_alloc;
-    const int wpb = b2c::UF_THREADS / 32;
-    const int grid = (int)std::max<long long>(1, std::min<long long>(c->uf_grid, (rows + wpb - 1) / wpb));
-    CK(c, cudaLaunchCooperativeKernel((const void *)b2c::k_hysteresis_uf, dim3(grid), dim3(b2c::UF_THREADS), args, (size_t)b2c::UF_SMEM, st));
-  } else {
-    CK(c, cudaLaunchCooperativeKernel((const void *)b2c::k_hysteresis, dim3(c->hyst_grid), dim3(b2c::HYST_THREADS), args, (size_t)c->hyst_smem, st));
-  }
-  c->launches++;
-  return B2C_OK;
 }
 
-// S plane -> u8 {0,255} edge map, nothing else
-int launch_expand(b2c_ctx *c, int n, uint8_t *edges, size_t edges_pitch, size_t edges_frame_stride, cudaStream_t st)
+// Union-find hysteresis of n frames from the planes the stencil wrote: three ordinary launches (tile, border,
+// resolve + expansion to the u8 map), no barrier inside, no host round trip between.  edges == null: bit plane E only.
+int launch_hysteresis(b2c_ctx *c, int n, uint8_t *edges, size_t edges_pitch, size_t edges_frame_stride, cudaStream_t st)
 {
   B2cHystParams p;
-  memset(&p, 0, sizeof(p));
-  p.S = S0(c);
-  p.C = C0(c);
-  p.plane_pitch = c->plane_pitch;
-  p.plane_frame_stride = plane_frame_stride(c);
-  p.w = c->w;
-  p.h = c->rows_alloc;
-  p.nframes = n;
-  p.edges = edges;
-  p.edges_pitch = (long long)edges_pitch;
-  p.edges_frame_stride = (long long)edges_frame_stride;
-  const long long groups = (long long)n * c->rows_alloc * ((c->w + 15) / 16);
-  const unsigned ge = (unsigned)std::max<long long>(1, std::min<long long>((groups + b2c::UFK_THREADS - 1) / b2c::UFK_THREADS, (long long)c->sm_count * 32));
-  b2c::k_uf_expand<<<ge, b2c::UFK_THREADS, 0, st>>>(p);
+  fill_hyst_params(c, p, n, edges, edges_pitch, edges_frame_stride);
+  const dim3 gt((c->wpr + b2c::UT_WORDS - 1) / b2c::UT_WORDS, (c->rows_alloc + b2c::UT_ROWS - 1) / b2c::UT_ROWS, n);
+  const bool pt = c->hyst_phase_timing;
+  const int T = b2c::UFK_THREADS;
+  if (pt) cudaEventRecord(c->ev_h[0], st);
+  b2c::k_uf_tile<<<gt, b2c::UT_THREADS, b2c::UT_SMEM, st>>>(p, c->d_blist, c->d_bcount, c->bcap);
+  if (pt) cudaEventRecord(c->ev_h[1], st);
+  // border list: typically ~12 % of bcap entries; 4 threads per entry, a quarter of the worst case in blocks, grid-stride for the rest
+  b2c::k_uf_border<<<dim3(std::max(1, (c->bcap + T - 1) / T), 1, n), T, 0, st>>>(p, c->d_blist, c->d_bcount, c->bcap);
+  if (pt) cudaEventRecord(c->ev_h[2], st);
+  const int tx = c->wpr >= 256 ? 256 : c->wpr > 32 ? 64 : 32, ty = 256 / tx;   // 256 threads = tx words x ty rows
+  const dim3 gr((c->wpr + tx - 1) / tx, (c->rows_alloc + 2 * ty - 1) / (2 * ty), n), br(tx, ty);   // a thread takes 2 rows
+  if (edges) b2c::k_uf_resolve<true><<<gr, br, 0, st>>>(p, c->d_bcount);
+  else b2c::k_uf_resolve<false><<<gr, br, 0, st>>>(p, c->d_bcount);
+  if (pt) cudaEventRecord(c->ev_h[3], st);
   CK(c, cudaGetLastError());
-  c->launches++;
+  c->launches += 3;
+  c->edges_valid = true;
   return B2C_OK;
 }
 
@@ -432,6 +375,8 @@ int b2c_create(b2c_handle *out, int device, int width, int height, int channels,
 int b2c_create_band(b2c_handle *out, int device, int width, int band_rows, int y0, int height_global)
 {
   if (!out || width < 1 || band_rows < 1 || y0 < 0 || y0 + band_rows > height_global) return B2C_ERR_INVALID;
+  // a band with a neighbour sends its first / last 4 rows as the neighbour's input halo: it must have them
+  if (band_rows < 4 && !(y0 == 0 && band_rows == height_global)) return B2C_ERR_INVALID;
   *out = nullptr;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
@@ -470,6 +415,7 @@ void b2c_destroy(b2c_handle c)
   cudaFree(c->d_map2);
   cudaFree(c->d_S_base);
   cudaFree(c->d_C_base);
+  cudaFree(c->d_E_base);
   cudaFree(c->d_edges);
   cudaFree(c->d_mono);
   cudaFree(c->d_blur);
@@ -479,14 +425,22 @@ void b2c_destroy(b2c_handle c)
   cudaFree(c->d_grad);
   cudaFree(c->d_flags);
   cudaFree(c->d_parent);
-  for (int k = 0; k < c->p2p_world; ++k)
-    if (k != c->p2p_rank && c->peer_mail[k]) cudaIpcCloseMemHandle(c->peer_mail[k]);
-  for (auto &q : c->peer_in)
-    if (q) cudaIpcCloseMemHandle(q);
+  if (c->peers_ipc) {
+    for (int k = 0; k < c->p2p_world; ++k)
+      if (k != c->p2p_rank && c->peer_mail[k]) cudaIpcCloseMemHandle(c->peer_mail[k]);
+    for (auto &q : c->peer_in)
+      if (q) cudaIpcCloseMemHandle(q);
+  }
   cudaFree(c->d_band_in);
   cudaFree(c->d_mailbox);
-  cudaFree(c->d_p2pctl);
-  if (c->h_p2pctl) cudaFreeHost(c->h_p2pctl);
+  cudaFree(c->d_seam_rec);
+  cudaFree(c->d_seam_roots);
+  cudaFree(c->d_seam_hkey);
+  cudaFree(c->d_seam_hval);
+  cudaFree(c->d_seam_P);
+  cudaFree(c->d_seam_pre);
+  cudaFree(c->d_seam_ctl);
+  if (c->h_seam_ctl) cudaFreeHost(c->h_seam_ctl);
   cudaFree(c->d_blist);
   cudaFree(c->d_bcount);
   cudaFree(c->d_zeros);
@@ -569,11 +523,13 @@ int b2c_run(b2c_handle c, const uint8_t *host_bgr, size_t row_stride, int final_
   if (final_stage == B2C_STAGE_HYSTER) {
     if ((rc = launch_stencil(c, c->d_in, c->in_row_stride, c->in_frame_stride, 1, st)) != B2C_OK) return rc;
     if (prof) CK(c, cudaEventRecord(c->ev_t[2], st));
-    if ((rc = launch_hysteresis(c, 1, c->d_edges, c->edges_pitch, c->edges_frame_stride, 0, 0, st)) != B2C_OK) return rc;
+    if ((rc = launch_hysteresis(c, 1, c->d_edges, c->edges_pitch, c->edges_frame_stride, st)) != B2C_OK) return rc;
     if (prof) CK(c, cudaEventRecord(c->ev_t[3], st));
   } else {
     // stage views: the pipeline stops after the selected stage (src/cvp/cannyEdgeH.cu:58-115)
     if ((rc = launch_stencil_emit(c, c->d_in, c->in_row_stride, st)) != B2C_OK) return rc;
+    c->edges_valid = false;   // the pipeline stops after the selected stage: no edge map of this frame exists
+    c->map2_valid = false;
     if (prof) CK(c, cudaEventRecord(c->ev_t[2], st));
     if (prof) CK(c, cudaEventRecord(c->ev_t[3], st));
     const int blocks = c->sm_count * 4;
@@ -614,12 +570,12 @@ int b2c_run_device(b2c_handle c, const uint8_t *dev_bgr, size_t row_stride, size
   int rc;
   if ((rc = launch_stencil(c, dev_bgr, row_stride, frame_stride, n, st)) != B2C_OK) return rc;
   if (prof) CK(c, cudaEventRecord(c->ev_t[2], st));
-  if ((rc = launch_hysteresis(c, n, dev_edges, edges_pitch, edges_frame_stride, 0, 0, st)) != B2C_OK) return rc;
+  if ((rc = launch_hysteresis(c, n, dev_edges, edges_pitch, edges_frame_stride, st)) != B2C_OK) return rc;
   if (prof) {
     CK(c, cudaEventRecord(c->ev_t[3], st));
     CK(c, cudaEventRecord(c->ev_t[4], st));
   }
-  c->last_in = dev_bgr;
+  c->last_in = nullptr;   // caller-owned memory: not retained (the stage accessors need a frame run through b2c_run)
   c->last_row_stride = row_stride;
   c->have_frame = true;
   c->stages_valid = false;
@@ -645,7 +601,7 @@ int b2c_hysteresis_device(b2c_handle c, int n, uint8_t *dev_edges, size_t edges_
     edges_pitch = c->edges_pitch;
     edges_frame_stride = c->edges_frame_stride;
   }
-  return launch_hysteresis(c, n, dev_edges, edges_pitch, edges_frame_stride, 0, 0, stream ? (cudaStream_t)stream : c->s_main);
+  return launch_hysteresis(c, n, dev_edges, edges_pitch, edges_frame_stride, stream ? (cudaStream_t)stream : c->s_main);
 }
 
 int b2c_run_batch_host(b2c_handle c, const uint8_t *frames, size_t row_stride, int n, uint8_t *edges_out, int packed_bits)
@@ -720,12 +676,12 @@ int b2c_run_batch_host(b2c_handle c, const uint8_t *frames, size_t row_stride, i
     if ((rc = launch_stencil(c, din, c->in_row_stride, c->in_frame_stride, cnt, c->s_main)) != B2C_OK) return rc;
     uint8_t *dedges = c->d_edges + (size_t)slot * slot_frames * c->edges_frame_stride;
     // all slots share the map / plane buffers: the compute stream serialises them
-    if ((rc = launch_hysteresis(c, cnt, dedges, c->edges_pitch, c->edges_frame_stride, 0, packed_bits ? 1 : 0, c->s_main)) != B2C_OK) return rc;
+    if ((rc = launch_hysteresis(c, cnt, packed_bits ? nullptr : dedges, c->edges_pitch, c->edges_frame_stride, c->s_main)) != B2C_OK) return rc;
     uint8_t *hout = out_pinned ? edges_out + (size_t)f0 * out_frame_host : c->h_out[slot];
     if (packed_bits) {
-      // the S planes are shared between slots, so the D2H of the bit planes stays on the compute stream
+      // the planes are shared between slots, so the D2H of the edge bit planes stays on the compute stream
       for (int f = 0; f < cnt; ++f)
-        CK(c, cudaMemcpy2DAsync(hout + (size_t)f * out_frame_host, out_row, S0(c) + (size_t)f * plane_frame_stride(c), (size_t)c->plane_pitch * 4, out_row, h, cudaMemcpyDeviceToHost, c->s_main));
+        CK(c, cudaMemcpy2DAsync(hout + (size_t)f * out_frame_host, out_row, E0(c) + (size_t)f * plane_frame_stride(c), (size_t)c->plane_pitch * 4, out_row, h, cudaMemcpyDeviceToHost, c->s_main));
       CK(c, cudaEventRecord(c->ev_k[slot], c->s_main));
       CK(c, cudaEventRecord(c->ev_out[slot], c->s_main));
     } else {
@@ -767,6 +723,9 @@ int b2c_get_buffer(b2c_handle c, int id, const void **dev_ptr, size_t *pitch_byt
   int es = 1;
   if (id >= B2C_BUF_MONO && id <= B2C_BUF_THRESH) {
     if (c->band) return B2C_ERR_UNSUPPORTED;
+    // the stage buffers are recomputed from the retained input: only frames that live in the handle's own input buffer
+    // qualify (a caller-owned device batch may be gone by now)
+    if (!c->last_in) return B2C_ERR_STATE;
     if (!c->stages_valid) {
       int rc = launch_stencil_emit(c, c->last_in, c->last_row_stride, c->s_main);
       if (rc != B2C_OK) return rc;
@@ -780,11 +739,21 @@ int b2c_get_buffer(b2c_handle c, int id, const void **dev_ptr, size_t *pitch_byt
     default: p = c->d_grad; pitch = (size_t)c->pitchf * 4; es = 4; break;
     }
   } else if (id == B2C_BUF_EDGES) {
+    if (!c->edges_valid) return B2C_ERR_STATE;   // the last run stopped before the hysteresis
     p = c->d_edges; pitch = c->edges_pitch;
   } else if (id == B2C_BUF_MAP2) {
+    if (!c->map2_valid) {   // the planes S and C are the map; this view is its accessor format
+      if (!c->d_map2) CK(c, cudaMalloc(&c->d_map2, (size_t)c->rows_alloc * c->map_pitch * 4));
+      b2c::k_planes_to_map2<<<c->sm_count * 2, 256, 0, c->s_main>>>(reinterpret_cast<const uint16_t *>(S0(c)), reinterpret_cast<const uint16_t *>(C0(c)), c->plane_pitch * 2, c->d_map2,
+                                                                   c->map_pitch, c->rows_alloc);
+      CK(c, cudaGetLastError());
+      c->launches++;
+      c->map2_valid = true;
+    }
     p = c->d_map2; pitch = (size_t)c->map_pitch * 4; es = 4;
   } else if (id == B2C_BUF_BITS) {
-    p = S0(c); pitch = (size_t)c->plane_pitch * 4; es = 4;
+    if (!c->edges_valid) return B2C_ERR_STATE;
+    p = E0(c); pitch = (size_t)c->plane_pitch * 4; es = 4;
   } else if (id == B2C_BUF_VIEW) {
     if (c->last_stage == B2C_STAGE_HYSTER) { p = c->d_edges; pitch = c->edges_pitch; }
     else { p = c->d_view; pitch = (size_t)c->w; }
@@ -874,6 +843,33 @@ int b2c_sync(b2c_handle c)
 }
 void *b2c_stream(b2c_handle c) { return c ? (void *)c->s_main : nullptr; }
 
+// A thresholded map (0 / 128 / 255, the reference's d_threshImage: cannyEdgeD.cu:274-292) from host memory into the
+// planes of frame 0, in place of a stencil run: hysteresis on maps produced elsewhere.  Blocking.
+int b2c_load_thresh(b2c_handle c, const uint8_t *host_thresh, size_t row_stride)
+{
+  if (!c || !host_thresh) return B2C_ERR_INVALID;
+  if (row_stride < (size_t)c->w) return B2C_ERR_SIZE;
+  DevGuard g(c->dev);
+  const int pp = c->plane_pitch, h = c->rows_alloc;
+  std::vector<uint32_t> S((size_t)pp * h, 0u), C((size_t)pp * h, 0u);
+  for (int y = 0; y < h; ++y) {
+    const uint8_t *r = host_thresh + (size_t)y * row_stride;
+    for (int x = 0; x < c->w; ++x) {
+      if (r[x] == 255) S[(size_t)y * pp + (x >> 5)] |= 1u << (x & 31);
+      if (r[x] >= 128) C[(size_t)y * pp + (x >> 5)] |= 1u << (x & 31);
+    }
+  }
+  CK(c, cudaStreamSynchronize(c->s_main));
+  CK(c, cudaMemcpy(S0(c), S.data(), S.size() * 4, cudaMemcpyHostToDevice));
+  CK(c, cudaMemcpy(C0(c), C.data(), C.size() * 4, cudaMemcpyHostToDevice));
+  c->have_frame = true;
+  c->stages_valid = false;
+  c->map2_valid = false;
+  c->edges_valid = false;
+  c->last_in = nullptr;
+  return B2C_OK;
+}
+
 // ---- row-band mode --------------------------------------------------------------------------------
 int b2c_band_stencil(b2c_handle c, const uint8_t *dev_bgr_band_row0, size_t row_stride, void *stream)
 {
@@ -885,31 +881,135 @@ int b2c_band_stencil(b2c_handle c, const uint8_t *dev_bgr_band_row0, size_t row_
   return launch_stencil(c, dev_bgr_band_row0, row_stride, 0, 1, st);
 }
 
-int b2c_band_hysteresis(b2c_handle c, int first_call, int write_edges, int *changed, void *stream)
+int b2c_band_hysteresis(b2c_handle c, void *stream)
 {
   if (!c || !c->band) return B2C_ERR_INVALID;
   DevGuard g(c->dev);
-  cudaStream_t st = stream ? (cudaStream_t)stream : c->s_main;
-  int rc;
-  if (write_edges == 2) {   // the bit plane is final: only expand it to the u8 edge map
-    rc = launch_expand(c, 1, c->d_edges, c->edges_pitch, c->edges_frame_stride, st);
-  } else {
-    if (!first_call) CK(c, cudaMemsetAsync(c->d_flags + 6, 0, sizeof(int), st));
-    rc = launch_hysteresis(c, 1, c->d_edges, c->edges_pitch, c->edges_frame_stride, first_call ? 0 : 1, write_edges ? 0 : 1, st);
-    // the cooperative kernels report "an edge bit was added" in flags[4]: same meaning at the fixpoint
-    if (rc == B2C_OK && !first_call && (c->hyst_impl != 0 || c->wpr > 1024))
-      CK(c, cudaMemcpyAsync(c->d_flags + 6, c->d_flags + 4, sizeof(int), cudaMemcpyDeviceToDevice, st));
-  }
-  if (rc != B2C_OK) return rc;
-  if (changed) {
-    CK(c, cudaMemcpyAsync(c->h_flags, c->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(c, cudaStreamSynchronize(st));
-    *changed = c->h_flags[4];
+  return launch_hysteresis(c, 1, c->d_edges, c->edges_pitch, c->edges_frame_stride, stream ? (cudaStream_t)stream : c->s_main);
+}
+
+namespace
+{
+// scratch of the seam kernels, allocated on first use
+int seam_alloc(b2c_ctx *c)
+{
+  if (c->d_seam_rec) return B2C_OK;
+  const int cap = b2c::seam_cap(c->wpr), hs = b2c::seam_hash_size(c->wpr);
+  CK(c, cudaMalloc(&c->d_seam_rec, b2c::seam_rec_words(c->wpr) * 4));
+  CK(c, cudaMemset(c->d_seam_rec, 0, b2c::seam_rec_words(c->wpr) * 4));
+  CK(c, cudaMalloc(&c->d_seam_roots, (size_t)2 * cap * sizeof(int)));
+  CK(c, cudaMalloc(&c->d_seam_hkey, (size_t)hs * sizeof(int)));
+  CK(c, cudaMalloc(&c->d_seam_hval, (size_t)hs * sizeof(int)));
+  CK(c, cudaMalloc(&c->d_seam_P, ((size_t)b2c::SEAM_MAXW * 2 * cap + 1) * sizeof(int)));
+  CK(c, cudaMalloc(&c->d_seam_pre, (size_t)b2c::SEAM_MAXW * 2 * c->wpr * sizeof(int)));
+  CK(c, cudaMalloc(&c->d_seam_ctl, 8 * sizeof(int)));
+  CK(c, cudaMemset(c->d_seam_ctl, 0, 8 * sizeof(int)));
+  CK(c, cudaMallocHost(&c->h_seam_ctl, 8 * sizeof(int)));
+  memset(c->h_seam_ctl, 0, 8 * sizeof(int));
+  const size_t dyn = b2c::seam_smem_bytes(c->wpr);
+  if (dyn > 48 * 1024) {
+    CK(c, cudaFuncSetAttribute(b2c::k_seam_publish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    CK(c, cudaFuncSetAttribute(b2c::k_seam_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   }
   return B2C_OK;
 }
+void fill_seam_band(b2c_ctx *c, b2c::B2cSeamBand &b)
+{
+  b.S = E0(c);   // "edges so far" of the band: strong | locally promoted
+  b.C = C0(c);
+  b.plane_pitch = c->plane_pitch;
+  b.wpr = c->wpr;
+  b.h = c->rows_alloc;
+  b.parent = c->d_parent;
+  b.roots = c->d_seam_roots;
+  b.hkey = c->d_seam_hkey;
+  b.hval = c->d_seam_hval;
+  b.hsize = b2c::seam_hash_size(c->wpr);
+  b.ctl = c->d_seam_ctl;
+}
+int seam_publish(b2c_ctx *c, uint32_t *rec, cudaStream_t st)
+{
+  b2c::B2cSeamBand b;
+  fill_seam_band(c, b);
+  c->seam_run += 1;
+  const size_t dyn = b2c::seam_smem_bytes(c->wpr);
+  b2c::k_seam_publish<<<1, b2c::SEAM_THREADS, dyn, st>>>(b, rec, c->seam_run);
+  CK(c, cudaGetLastError());
+  c->launches++;
+  return B2C_OK;
+}
+// solve on the gathered records + one resolve pass that promotes the components the solve hung under node 0
+int seam_solve(b2c_ctx *c, const uint32_t *const *recs, int world, int rank, cudaStream_t st)
+{
+  b2c::B2cSeamBand b;
+  fill_seam_band(c, b);
+  b2c::B2cSeamAll a;
+  memset(&a, 0, sizeof(a));
+  for (int r = 0; r < world; ++r) a.rec[r] = recs[r];
+  a.world = world;
+  a.rank = rank;
+  a.P = c->d_seam_P;
+  a.pre = c->d_seam_pre;
+  const size_t dyn = b2c::seam_smem_bytes(c->wpr);
+  b2c::k_seam_solve<<<1, b2c::SEAM_THREADS, dyn, st>>>(b, a);
+  B2cHystParams p;
+  fill_hyst_params(c, p, 1, c->d_edges, c->edges_pitch, c->edges_frame_stride);
+  p.need = c->d_seam_ctl;   // ctl[0]: a root of this band was promoted
+  const int tx = c->wpr >= 256 ? 256 : c->wpr > 32 ? 64 : 32, ty = 256 / tx;
+  const dim3 gr((c->wpr + tx - 1) / tx, (c->rows_alloc + 2 * ty - 1) / (2 * ty), 1), br(tx, ty);
+  b2c::k_uf_resolve<true, true><<<gr, br, 0, st>>>(p, c->d_bcount);
+  CK(c, cudaGetLastError());
+  c->launches += 2;
+  return B2C_OK;
+}
+}// namespace
 
-// ---- peer-to-peer rounds (see k_band_p2p.cuh) -----------------------------------------------------------------
+int b2c_band_seam_bytes(b2c_handle c, size_t *bytes)
+{
+  if (!c || !c->band || !bytes) return B2C_ERR_INVALID;
+  *bytes = b2c::seam_rec_words(c->wpr) * 4;
+  return B2C_OK;
+}
+
+int b2c_band_seam_publish(b2c_handle c, void **record_dev, void *stream)
+{
+  if (!c || !c->band || !record_dev) return B2C_ERR_INVALID;
+  DevGuard g(c->dev);
+  int rc = seam_alloc(c);
+  if (rc != B2C_OK) return rc;
+  *record_dev = c->d_seam_rec;
+  return seam_publish(c, c->d_seam_rec, stream ? (cudaStream_t)stream : c->s_main);
+}
+
+int b2c_band_seam_solve(b2c_handle c, const void *all_records_dev, int world, int rank, void *stream)
+{
+  if (!c || !c->band || !all_records_dev || world < 1 || world > b2c::SEAM_MAXW || rank < 0 || rank >= world) return B2C_ERR_INVALID;
+  DevGuard g(c->dev);
+  int rc = seam_alloc(c);
+  if (rc != B2C_OK) return rc;
+  const uint32_t *recs[b2c::SEAM_MAXW];
+  const size_t stride = b2c::seam_rec_words(c->wpr);
+  for (int r = 0; r < world; ++r) recs[r] = (const uint32_t *)all_records_dev + (size_t)r * stride;
+  return seam_solve(c, recs, world, rank, stream ? (cudaStream_t)stream : c->s_main);
+}
+
+int b2c_band_status(b2c_handle c, int *promoted_runs, int *error)
+{
+  if (!c || !c->band) return B2C_ERR_INVALID;
+  DevGuard g(c->dev);
+  if (!c->d_seam_ctl) {
+    if (promoted_runs) *promoted_runs = 0;
+    if (error) *error = 0;
+    return B2C_OK;
+  }
+  CK(c, cudaMemcpyAsync(c->h_seam_ctl, c->d_seam_ctl, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->s_main));
+  CK(c, cudaStreamSynchronize(c->s_main));
+  if (promoted_runs) *promoted_runs = c->h_seam_ctl[3];
+  if (error) *error = c->h_seam_ctl[2];
+  return B2C_OK;
+}
+
+// ---- peer-to-peer exchange for ranks of one box (see k_band_p2p.cuh / k_band_seam.cuh) -------------------------------
 int b2c_band_input(b2c_handle c, void **dev_ptr, size_t *row_stride)
 {
   if (!c || !c->band || !dev_ptr) return B2C_ERR_INVALID;
@@ -924,21 +1024,27 @@ int b2c_band_input(b2c_handle c, void **dev_ptr, size_t *row_stride)
   return B2C_OK;
 }
 
+namespace
+{
+int p2p_alloc(b2c_ctx *c)
+{
+  if (c->d_mailbox) return B2C_OK;
+  const size_t bytes = b2c::bp_mailbox_words(c->wpr) * sizeof(uint32_t);
+  CK(c, cudaMalloc(&c->d_mailbox, bytes));
+  CK(c, cudaMemset(c->d_mailbox, 0, bytes));
+  void *in;
+  int rc = b2c_band_input(c, &in, nullptr);
+  if (rc != B2C_OK) return rc;
+  return seam_alloc(c);
+}
+}// namespace
+
 int b2c_band_p2p_export(b2c_handle c, void *blob_144)
 {
   if (!c || !c->band || !blob_144) return B2C_ERR_INVALID;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   DevGuard g(c->dev);
-  if (!c->d_mailbox) {
-    const size_t bytes = b2c::bp_mailbox_words(c->wpr) * sizeof(uint32_t);
-    CK(c, cudaMalloc(&c->d_mailbox, bytes));
-    CK(c, cudaMemset(c->d_mailbox, 0, bytes));
-    CK(c, cudaMalloc(&c->d_p2pctl, 64 * sizeof(int)));
-    CK(c, cudaMemset(c->d_p2pctl, 0, 64 * sizeof(int)));
-    CK(c, cudaMallocHost(&c->h_p2pctl, 8 * sizeof(int)));
-  }
-  void *in;
-  int rc = b2c_band_input(c, &in, nullptr);
+  int rc = p2p_alloc(c);
   if (rc != B2C_OK) return rc;
   cudaIpcMemHandle_t h[2];
   CK(c, cudaIpcGetMemHandle(&h[0], c->d_mailbox));
@@ -969,6 +1075,39 @@ int b2c_band_p2p_open(b2c_handle c, const void *all_blobs, int world, int rank)
       if (k == rank - 1) memcpy(&c->peer_rows_up, blob + 128, sizeof(int));
     }
   }
+  c->peers_ipc = true;
+  c->p2p_world = world;
+  c->p2p_rank = rank;
+  return B2C_OK;
+}
+
+// the same wiring for bands that live in ONE process (any devices with peer access, or one device): the "peers" are
+// the other handles themselves.  Used by single-process drivers and by the single-GPU test of the peer-to-peer kernels.
+int b2c_band_p2p_open_local(b2c_handle c, const b2c_handle *all_handles, int world, int rank)
+{
+  if (!c || !c->band || !all_handles || world < 2 || world > b2c::BP_MAXW || rank < 0 || rank >= world || all_handles[rank] != c) return B2C_ERR_INVALID;
+  DevGuard g(c->dev);
+  for (int k = 0; k < world; ++k) {
+    b2c_ctx *o = all_handles[k];
+    if (!o || !o->band || o->w != c->w) return B2C_ERR_INVALID;
+    {
+      DevGuard g2(o->dev);
+      int rc = p2p_alloc(o);
+      if (rc != B2C_OK) return rc;
+    }
+    if (o->dev != c->dev) {
+      int can = 0;
+      CK(c, cudaDeviceCanAccessPeer(&can, c->dev, o->dev));
+      if (!can) return B2C_ERR_UNSUPPORTED;
+      cudaError_t e = cudaDeviceEnablePeerAccess(o->dev, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return set_err(c, e, "cudaDeviceEnablePeerAccess");
+      (void)cudaGetLastError();
+    }
+    c->peer_mail[k] = o->d_mailbox;
+    if (k == rank - 1) { c->peer_in[0] = o->d_band_in; c->peer_rows_up = o->rows_alloc; }
+    if (k == rank + 1) c->peer_in[1] = o->d_band_in;
+  }
+  c->peers_ipc = false;
   c->p2p_world = world;
   c->p2p_rank = rank;
   return B2C_OK;
@@ -983,7 +1122,7 @@ void fill_p2p(b2c_ctx *c, b2c::B2cBandP2P &q)
   q.world = c->p2p_world;
   q.rank = c->p2p_rank;
   q.wpr = c->wpr;
-  q.ctl = c->d_p2pctl;
+  q.ctl = c->d_seam_ctl;
   q.in_up = (uint8_t *)c->peer_in[0];
   q.in_dn = (uint8_t *)c->peer_in[1];
   q.in_own = c->d_band_in;
@@ -995,94 +1134,64 @@ void fill_p2p(b2c_ctx *c, b2c::B2cBandP2P &q)
 }// namespace
 
 // the 4 input rows on either side of every seam, stored straight into the neighbours' band input buffers; returns
-// (asynchronously) once both neighbours' rows have landed in this band's buffer
-int b2c_band_p2p_halo(b2c_handle c, void *stream)
+// (asynchronously) once both neighbours' rows have landed in this band's buffer.  phase: B2C_P2P_ALL, or B2C_P2P_PUSH
+// then B2C_P2P_WAIT (a single-process driver of several bands issues ALL pushes before the first wait: a device-side
+// wait must never be queued ahead of the store it waits for).
+int b2c_band_p2p_halo(b2c_handle c, void *stream, int phase)
 {
-  if (!c || !c->band || c->p2p_world < 2 || !c->d_band_in) return B2C_ERR_INVALID;
+  if (!c || !c->band || c->p2p_world < 2 || !c->d_band_in || phase < B2C_P2P_ALL || phase > B2C_P2P_WAIT) return B2C_ERR_INVALID;
   DevGuard g(c->dev);
   cudaStream_t st = stream ? (cudaStream_t)stream : c->s_main;
   b2c::B2cBandP2P q;
   fill_p2p(c, q);
   const int cpr = (c->w * 3 + 15) / 16, nblocks = (4 * cpr + 255) / 256;
-  c->p2p_run += 1;
-  b2c::k_band_push_halo<<<dim3(nblocks, 2), 256, 0, st>>>(q);
-  b2c::k_band_wait_halo<<<1, 1, 0, st>>>(q, c->p2p_run, nblocks);
+  if (phase != B2C_P2P_WAIT) {
+    c->p2p_run += 1;
+    CK(c, cudaMemsetAsync(c->d_seam_ctl + 2, 0, sizeof(int), st));   // a time-out of an earlier run is not sticky
+    b2c::k_band_push_halo<<<dim3(nblocks, 2), 256, 0, st>>>(q);
+    c->launches++;
+  }
+  if (phase != B2C_P2P_PUSH) {
+    b2c::k_band_wait_halo<<<1, 1, 0, st>>>(q, c->p2p_run, nblocks);
+    c->launches++;
+  }
   CK(c, cudaGetLastError());
-  c->launches += 2;
   return B2C_OK;
 }
 
-int b2c_band_p2p_converge(b2c_handle c, int rounds_per_sync, int *rounds_out, void *stream)
+// cross-band hysteresis over peer memory: my seam record -> every rank's mailbox, wait for all records, solve, resolve.
+// Asynchronous on `stream`; b2c_band_status reports a peer time-out.  phase as above.
+int b2c_band_p2p_seam(b2c_handle c, void *stream, int phase)
 {
-  if (!c || !c->band || c->p2p_world < 2 || rounds_per_sync < 1) return B2C_ERR_INVALID;
-  if (c->hyst_impl != 0 || c->wpr > 1024) return B2C_ERR_UNSUPPORTED;
+  if (!c || !c->band || c->p2p_world < 2 || !c->d_mailbox || phase < B2C_P2P_ALL || phase > B2C_P2P_WAIT) return B2C_ERR_INVALID;
   DevGuard g(c->dev);
   cudaStream_t st = stream ? (cudaStream_t)stream : c->s_main;
-  B2cHystParams p;
-  memset(&p, 0, sizeof(p));
-  p.S = S0(c);
-  p.C = C0(c);
-  p.plane_pitch = c->plane_pitch;
-  p.plane_frame_stride = plane_frame_stride(c);
-  p.w = c->w;
-  p.h = c->rows_alloc;
-  p.nframes = 1;
-  p.flags = c->d_flags;
-  p.parent = c->d_parent;
-  p.parent_frame_stride = (long long)c->rows_alloc * c->plane_pitch * 32;
-  p.edges = c->d_edges;   // every resolve also (re)writes the u8 edge map: no separate expansion pass after convergence
-  p.edges_pitch = (long long)c->edges_pitch;
-  p.edges_frame_stride = (long long)c->edges_frame_stride;
-  p.skip = c->d_p2pctl + b2c::BP_DONE;
-  p.need = c->d_p2pctl + b2c::BP_SEEDED;   // set by this round's seed kernel iff something new was seeded in this band
-  b2c::B2cBandP2P q;
-  fill_p2p(c, q);
-  // start of a run: not done, no rounds yet, "seeded" forced on so that the first exchange is always evaluated
-  CK(c, cudaMemsetAsync(c->d_p2pctl + b2c::BP_DONE, 0, sizeof(int), st));
-  CK(c, cudaMemsetAsync(c->d_p2pctl + b2c::BP_RUN_ROUNDS, 0, sizeof(int), st));
-  CK(c, cudaMemsetAsync(c->d_p2pctl + b2c::BP_SEEDED, 0, sizeof(int), st));
-  CK(c, cudaMemsetAsync(c->d_p2pctl + b2c::BP_SEEDED, 1, 1, st));
-  int per_sm = 0;
-  CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b2c::k_band_rounds<true>, 256, 0));
-  if (per_sm < 1) return B2C_ERR_CUDA;
-  const long long nwords = (long long)c->rows_alloc * c->wpr;
-  const int grid = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * std::min(per_sm, 4), (nwords + 255) / 256));
-  int max_rounds = std::max(rounds_per_sync, 1);
-  void *args[] = { &p, &q, &max_rounds };
-  for (int total = 0; total < 4096; total += max_rounds) {
-    CK(c, cudaLaunchCooperativeKernel((const void *)b2c::k_band_rounds<true>, dim3(grid), dim3(256), args, 0, st));
-    c->launches += 1;
-    CK(c, cudaMemcpyAsync(c->h_p2pctl, c->d_p2pctl, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(c, cudaStreamSynchronize(st));
-    if (c->h_p2pctl[b2c::BP_ERROR]) {
-      c->last_err = "row-band peer-to-peer round timed out waiting for another rank";
-      return B2C_ERR_STATE;
+  const int world = c->p2p_world, rank = c->p2p_rank;
+  uint32_t *mine = (uint32_t *)c->peer_mail[rank];
+  if (phase != B2C_P2P_WAIT) {
+    const int par = (c->seam_run + 1) & 1;   // seam_publish increments seam_run
+    int rc = seam_publish(c, mine + b2c::bp_seam_slot(c->wpr, par, rank), st);
+    if (rc != B2C_OK) return rc;
+    b2c::B2cSeamPeers q;
+    memset(&q, 0, sizeof(q));
+    for (int k = 0; k < world; ++k) {
+      q.slot[k] = (uint32_t *)c->peer_mail[k] + b2c::bp_seam_slot(c->wpr, par, rank);
+      q.flag[k] = (uint32_t *)c->peer_mail[k] + b2c::bp_seam_flag(c->wpr, par, rank);
     }
-    if (c->h_p2pctl[b2c::BP_DONE]) break;
+    q.world = world;
+    q.rank = rank;
+    b2c::k_seam_push<<<world, b2c::SEAM_THREADS, 0, st>>>(q, c->wpr, c->seam_run);
+    CK(c, cudaGetLastError());
+    c->launches++;
   }
-  if (rounds_out) *rounds_out = c->h_p2pctl[b2c::BP_RUN_ROUNDS];
-  return c->h_p2pctl[b2c::BP_DONE] ? B2C_OK : B2C_ERR_STATE;
-}
-
-int b2c_band_boundary_ptr(b2c_handle c, int which, void **dev_ptr, int *words)
-{
-  if (!c || !c->band || !dev_ptr || which < 0 || which > 1) return B2C_ERR_INVALID;
-  *dev_ptr = S0(c) + (which == 0 ? 0 : (size_t)(c->rows_alloc - 1) * c->plane_pitch);
-  if (words) *words = c->wpr;
-  return B2C_OK;
-}
-int b2c_band_ghost_ptr(b2c_handle c, int which, void **dev_ptr, int *words)
-{
-  if (!c || !c->band || !dev_ptr || which < 0 || which > 1) return B2C_ERR_INVALID;
-  *dev_ptr = which == 0 ? c->d_S_base : S0(c) + (size_t)c->rows_alloc * c->plane_pitch;
-  if (words) *words = c->wpr;
-  return B2C_OK;
-}
-int b2c_band_flag_ptr(b2c_handle c, void **dev_ptr)
-{
-  if (!c || !dev_ptr) return B2C_ERR_INVALID;
-  *dev_ptr = c->d_flags + 6;
-  return B2C_OK;
+  if (phase == B2C_P2P_PUSH) return B2C_OK;
+  const int par = c->seam_run & 1;
+  b2c::k_seam_wait<<<1, 32, 0, st>>>(mine + b2c::bp_seam_flag(c->wpr, par, 0), world, c->seam_run, c->d_seam_ctl);
+  CK(c, cudaGetLastError());
+  c->launches++;
+  const uint32_t *recs[b2c::SEAM_MAXW];
+  for (int r = 0; r < world; ++r) recs[r] = mine + b2c::bp_seam_slot(c->wpr, par, r);
+  return seam_solve(c, recs, world, rank, st);
 }
 
 // ---- misc -----------------------------------------------------------------------------------------
@@ -1140,35 +1249,11 @@ int b2c_set_option(b2c_handle c, const char *name, int value)
     c->march_rb = value;
     return B2C_OK;
   }
-  if (!strcmp(name, "hyst_impl")) {
-    if (value < 0 || value > 2) return B2C_ERR_INVALID;
-    c->hyst_impl = value;
-    return B2C_OK;
-  }
-  if (!strcmp(name, "hyst_max_rounds")) {
-    if (value < 1) return B2C_ERR_INVALID;
-    c->hyst_max_rounds = value;
-    return B2C_OK;
-  }
   return B2C_ERR_INVALID;
 }
 int b2c_get_info(b2c_handle c, const char *name)
 {
   if (!c || !name) return B2C_ERR_INVALID;
-  if (!strcmp(name, "hyst_rounds")) return c->h_flags[3];
-  if (!strncmp(name, "stamp", 5)) {   // phase time stamps of the last hysteresis launch (ns, low 32 bits); debugging aid
-    int v[16];
-    if (cudaMemcpy(v, c->d_flags, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return B2C_ERR_CUDA;
-    const int k = name[5] - '0';
-    return (k >= 0 && k < 8) ? v[8 + k] : B2C_ERR_INVALID;
-  }
-  if (!strncmp(name, "p2p_stamp", 9)) {   // time stamps of the last k_band_rounds launch (ns, low 32 bits); "p2p_stamp55" = how many
-    const int k = atoi(name + 9);
-    int v = 0;
-    if (!c->d_p2pctl || k < 0 || k > 55) return B2C_ERR_INVALID;
-    if (cudaMemcpy(&v, c->d_p2pctl + 8 + k, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return B2C_ERR_CUDA;
-    return v;
-  }
   if (!strncmp(name, "hyst_phase_us", 13)) {   // phase times of the last union-find hysteresis run with "hyst_phase_timing" on (us)
     const int k = name[13] - '0';
     if (k < 0 || k > 2 || !c->ev_h[0]) return B2C_ERR_INVALID;
@@ -1176,7 +1261,6 @@ int b2c_get_info(b2c_handle c, const char *name)
     if (cudaEventSynchronize(c->ev_h[3]) != cudaSuccess || cudaEventElapsedTime(&ms, c->ev_h[k], c->ev_h[k + 1]) != cudaSuccess) return B2C_ERR_CUDA;
     return (int)(ms * 1000.0f + 0.5f);
   }
-  if (!strcmp(name, "hyst_grid")) return c->hyst_grid;
   if (!strcmp(name, "sm_count")) return c->sm_count;
   if (!strcmp(name, "stencil_impl")) return c->stencil_impl;
   if (!strcmp(name, "march_ctas_per_sm")) return c->march_ctas_per_sm;

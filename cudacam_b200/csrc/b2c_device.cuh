@@ -2,13 +2,13 @@
 //
 // Data formats (all device-resident, see DESIGN.md "Data layout in HBM"):
 //   BGR8 input      : interleaved bytes, byte 0 = B (reference: src/cvp/cannyEdgeD.cu:14-19,66-67)
-//   2-bit map       : one u32 per 16 horizontally adjacent pixels; bit i (0..15) = STRONG flag of pixel
-//                     16*g+i, bit 16+i = WEAK-only flag.  Equivalent of the reference's d_thresh
-//                     {0,128,255} (src/cvp/cannyEdgeD.cu:273-293) at 2 bits per pixel.
-//   bit planes S, C : one u32 per 32 pixels (bit i = pixel 32*k+i); S = final edges so far,
-//                     C = candidates (weak|strong).  Rows -1 and h of every frame are ghost rows
-//                     (zero for a whole image = the reference's zero padding, cannyEdgeD.cu:322-329;
-//                     the neighbour band's boundary row in row-band mode).
+//   bit planes S, C : one u32 per 32 pixels (bit i = pixel 32*k+i); S = strong, C = candidates (weak|strong): the two
+//                     planes ARE the 2-bit weak/strong map, the equivalent of the reference's d_thresh {0,128,255}
+//                     (src/cvp/cannyEdgeD.cu:273-293) at 2 bits per pixel, written by the stencil kernel.  Rows -1
+//                     and h of every frame are zero ghost rows (= the reference's zero padding, cannyEdgeD.cu:322-329).
+//   bit plane E     : edges = S | weak pixels promoted by the hysteresis (written by the resolve kernel).
+//   2-bit map view  : one u32 per 16 pixels, bit i = strong flag of pixel 16*g+i, bit 16+i = weak-only flag
+//                     (accessor format B2C_BUF_MAP2, made from the planes on demand).
 //   edges           : u8 {0,255} per pixel = the reference's d_hyster after removeCandidates
 //                     (src/cvp/cannyEdgeD.cu:379-395).
 #pragma once
@@ -43,9 +43,11 @@ struct B2cStencilParams {
                              // outside [0,h_glob), real neighbour rows are read inside it)
   int nframes;
   int channels;              // bytes per input pixel: 3 = BGR8, 4 = BGRA8 (alpha ignored), 1 = GRAY8
-  uint32_t *map2;            // 2-bit map out
-  int map_pitch;             // u32 per row
-  long long map_frame_stride;// u32 per frame
+  // out: the two bit planes of the 2-bit weak/strong map, as 16-bit halves (one u16 per 16 pixels: strips are 15
+  // such groups wide): S = strong, C = weak | strong; row 0 of frame 0
+  uint16_t *pl_S, *pl_C;
+  int pl_pitch16;            // u16 per plane row
+  long long pl_frame_stride16;
   unsigned lo, hi;           // thresholds (src/cvp/cannyEdgeH.cu:22-23, strict '>' cannyEdgeD.cu:290)
   float gk[25];              // k*(1/159.0f) rounded on the host (src/cvp/cannyEdgeH.cu:372-379)
   // double threshold in the N = sumX^2+sumY^2 domain.  The reference thresholds v = (unsigned char)grad
@@ -61,10 +63,8 @@ struct B2cStencilParams {
 };
 
 struct B2cHystParams {
-  const uint32_t *map2;
-  int map_pitch;
-  long long map_frame_stride;
-  uint32_t *S, *C;           // row 0 of frame 0; row -1 / row h are ghost rows
+  const uint32_t *S, *C;     // planes written by the stencil: strong, weak | strong; row 0 of frame 0; rows -1 / h are zero ghost rows
+  uint32_t *E;               // edges = S | promoted weak pixels (written by the resolve kernel), same geometry
   int plane_pitch;           // u32 per row
   long long plane_frame_stride;
   int w, h, nframes;

@@ -1,4 +1,4 @@
-// k_hysteresis_uf.cuh -- on-device hysteresis as ONE cooperative launch with a constant number of phases.
+// k_hysteresis_uf.cuh -- on-device hysteresis: union-find over the weak pixels, three ordinary launches, no host round trip.
 //
 // Replaces the reference's CPU-driven relaunch loop (src/cvp/cannyEdgeH.cu:297-338: 1 + up to 100 launches of
 // `hysteresis`, two blocking 4-byte memcpys per launch) and `removeCandidates` (src/cvp/cannyEdgeD.cu:379-395).
@@ -6,14 +6,11 @@
 // fixpoint is "weak pixels that are 8-connected to a strong pixel through weak pixels survive".  That is a
 // connected-components question, answered here without rounds by a lock-free union-find over the WEAK pixels only
 // (~0.7 % of a frame), with one virtual node 0 = "touches a strong pixel":
-//   A. bit planes S (strong) and C (weak|strong) from the 2-bit map, 32 pixels per word;
-//   B. init: every weak pixel gets parent = first pixel of its horizontal run inside the word (runs are born
-//      flat), or 0 if any pixel of the run has a strong 8-neighbour (3x3 dilation of S done on words);
-//   C. union: every weak pixel is united with its weak W / NW / N / NE neighbours (atomicMin links the larger
-//      root under the smaller one, so 0 always wins);
-//   D. resolve: a weak pixel is an edge iff find() == 0; S |= those bits;
-//   E. expand S to the u8 {0,255} map the reference hands to its PBO.
-// Phases are separated by grid-wide barriers inside the launch; nothing returns to the host.
+//   planes S (strong) and C (weak|strong), 32 pixels per word (written by the stencil kernel);
+//   every horizontal run of weak pixels inside a word is a node; a run that touches a strong pixel (3x3 dilation of S
+//   done on words) starts under node 0;
+//   unions with the weak W / NW / N / NE neighbours (atomicMin links the larger root under the smaller one, so 0 wins);
+//   resolve: a run is an edge iff find() == 0; S |= those bits; S expands to the u8 {0,255} map of the reference's PBO.
 // Parent words that other CTAs may update are read with ld.global.cg (L2).
 #pragma once
 #include "b2c_device.cuh"
@@ -77,33 +74,7 @@ __device__ __forceinline__ int uf_run_head(uint32_t X, int k)
 // rank of the run that starts at bit hb among the runs of word X (a 32-bit word holds at most 16 runs)
 __device__ __forceinline__ int uf_run_rank(uint32_t X, int hb) { return __popc(X & ~(X << 1) & ((1u << hb) - 1u)); }
 
-// ---- per-word bodies of the three sparse phases -------------------------------------------------------------------
-// B: parents of the weak pixels of one word
-__device__ __forceinline__ void uf_init_word(const B2cHystParams &p, int f, int y, int xw, uint32_t wd, uint32_t sM, int W32)
-{
-  const int pp = p.plane_pitch;
-  const uint32_t *Sr = p.S + f * p.plane_frame_stride + (long long)y * pp + xw;
-  const uint32_t v = __ldcg(Sr - pp) | sM | __ldcg(Sr + pp);
-  const uint32_t vl = xw > 0 ? (__ldcg(Sr - pp - 1) | __ldcg(Sr - 1) | __ldcg(Sr + pp - 1)) : 0u;
-  const uint32_t vr = xw + 1 < pp ? (__ldcg(Sr - pp + 1) | __ldcg(Sr + 1) | __ldcg(Sr + pp + 1)) : 0u;
-  const uint32_t near = wd & (v | (v << 1) | (v >> 1) | (vl >> 31) | (vr << 31));
-  int *P = p.parent + f * p.parent_frame_stride;
-  const int base = y * W32 + xw * 32;
-  uint32_t m = wd;
-  while (m) {
-    const uint32_t lo = m & (0u - m);
-    const uint32_t run = m & ~(m + lo);   // the run of ones that starts at the lowest set bit
-    m &= ~run;
-    const int val = (run & near) ? 0 : base + __ffs((int)lo);
-    uint32_t r = run;
-    while (r) {
-      const int b = __ffs((int)r) - 1;
-      r &= r - 1u;
-      P[base + b] = val;
-    }
-  }
-}
-
+// ---- per-word bodies -----------------------------------------------------------------------------------------
 // C: one union per (run, touching fragment of the row above / previous word): a run already shares one parent.
 // doW / doN / doNW / doNE select which adjacencies are united here (the tile kernel has already united the ones that
 // stay inside a tile).
@@ -141,164 +112,14 @@ __device__ __forceinline__ void uf_union_word(const B2cHystParams &p, int f, int
   }
 }
 
-// D: a run survives iff its root is node 0; returns true if the word gained edge bits
-__device__ __forceinline__ bool uf_resolve_word(const B2cHystParams &p, int f, int y, int xw, int W32)
-{
-  const long long o = f * p.plane_frame_stride + (long long)y * p.plane_pitch + xw;
-  const uint32_t s = p.S[o];
-  uint32_t m = p.C[o] & ~s;
-  if (m == 0u) return false;
-  int *P = p.parent + f * p.parent_frame_stride;
-  const int base = y * W32 + xw * 32 + 1;
-  uint32_t add = 0u;
-  while (m) {
-    const uint32_t lo = m & (0u - m);
-    const uint32_t run = m & ~(m + lo);
-    m &= ~run;
-    if (uf_find_final(P, base + __ffs((int)lo) - 1) == 0) add |= run;
-  }
-  if (add) p.S[o] = s | add;
-  return add != 0u;
-}
-
-#ifndef B2C_EMU
-__device__ __forceinline__ unsigned b2c_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return (unsigned)t; }
-#define B2C_STAMP(k) do { if (gtid == 0) p.flags[8 + (k)] = (int)b2c_gtime(); } while (0)
-#else
-#define B2C_STAMP(k) do { } while (0)
-#endif
-
-constexpr int UF_LIST_CAP = 512;   // words with weak pixels remembered per warp (2 KB of shared memory)
-constexpr int UF_SMEM = (UF_THREADS / 32) * UF_LIST_CAP * 4;
-
-__global__ void __launch_bounds__(UF_THREADS) k_hysteresis_uf(const B2cHystParams p)
-{
-  B2C_DYN_SMEM(smem);
-  const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (long long)gridDim.x * blockDim.x;
-  const int wpr = (p.w + 31) >> 5;
-  const int W32 = p.plane_pitch * 32;   // node id = y * W32 + x + 1 (0 = "touches strong")
-  // one warp per plane row: (frame, y) from a 32-bit division per row, lanes stride over the row's words
-  const int lane = threadIdx.x & 31;
-  const int gwarp = (int)(gtid >> 5), nwarps = (int)(gthreads >> 5);
-  const int nrows = p.nframes * p.h;
-  // Words that hold weak pixels are ~10 % of a plane: phase B remembers them per warp (shared memory survives
-  // the grid barriers), so that the latency-bound phases C and D run with every lane busy.
-  uint32_t *wlist = reinterpret_cast<uint32_t *>(smem) + (threadIdx.x >> 5) * UF_LIST_CAP;
-  int wcnt = 0;
-  bool wovf = wpr > 1024;
-#define B2C_FOR_WORDS                                            \
-  for (int row_ = gwarp; row_ < nrows; row_ += nwarps)           \
-    for (int xw = lane, f = row_ / p.h, y = row_ - f * p.h; xw < wpr; xw += 32)
-
-  B2C_STAMP(0);
-  // ---- A: bit planes ----
-  if (!p.skip_init) {
-    B2C_FOR_WORDS {
-      const uint32_t *mrow = p.map2 + f * p.map_frame_stride + (long long)y * p.map_pitch;
-      const uint32_t m0 = mrow[2 * xw], m1 = (2 * xw + 1 < p.map_pitch) ? mrow[2 * xw + 1] : 0u;
-      const uint32_t s = (m0 & 0xFFFFu) | (m1 << 16), wk = (m0 >> 16) | (m1 & 0xFFFF0000u);
-      const long long o = f * p.plane_frame_stride + (long long)y * p.plane_pitch + xw;
-      p.S[o] = s;
-      p.C[o] = s | wk;
-    }
-  }
-  if (gtid == 0) { p.flags[3] = 1; p.flags[4] = 0; }
-  __threadfence();
-  B2C_GRID_SYNC();
-
-  B2C_STAMP(1);
-  // ---- B: parents of the weak pixels; remember the words that have any ----
-  for (int row_ = gwarp; row_ < nrows; row_ += nwarps) {
-    const int f = row_ / p.h, y = row_ - f * p.h;
-    for (int xw0 = 0; xw0 < wpr; xw0 += 32) {
-      const int xw = xw0 + lane;
-      uint32_t wd = 0u, sM = 0u;
-      if (xw < wpr) {
-        const long long o = f * p.plane_frame_stride + (long long)y * p.plane_pitch + xw;
-        sM = __ldcg(p.S + o);
-        wd = __ldcg(p.C + o) & ~sM;
-      }
-      if (wd) uf_init_word(p, f, y, xw, wd, sM, W32);
-      const uint32_t mask = __ballot_sync(B2C_FULL, wd != 0u);
-      if (!wovf) {
-        const int add = __popc(mask);
-        if (wcnt + add > UF_LIST_CAP) wovf = true;
-        else {
-          if (wd) wlist[wcnt + __popc(mask & ((1u << lane) - 1u))] = ((uint32_t)row_ << 10) | (uint32_t)xw;
-          wcnt += add;
-        }
-      }
-    }
-  }
-  __threadfence();
-  B2C_GRID_SYNC();
-
-  B2C_STAMP(2);
-  // ---- C: unions ----
-  if (!wovf) {
-    __syncwarp();
-    for (int i = lane; i < wcnt; i += 32) {
-      const uint32_t e = wlist[i];
-      const int row_ = (int)(e >> 10), f = row_ / p.h;
-      uf_union_word(p, f, row_ - f * p.h, (int)(e & 1023u), W32);
-    }
-  } else {
-    B2C_FOR_WORDS uf_union_word(p, f, y, xw, W32);
-  }
-  __threadfence();
-  B2C_GRID_SYNC();
-
-  B2C_STAMP(3);
-  // ---- D: resolve ----
-  bool changed = false;
-  if (!wovf) {
-    for (int i = lane; i < wcnt; i += 32) {
-      const uint32_t e = wlist[i];
-      const int row_ = (int)(e >> 10), f = row_ / p.h;
-      changed |= uf_resolve_word(p, f, row_ - f * p.h, (int)(e & 1023u), W32);
-    }
-  } else {
-    B2C_FOR_WORDS changed |= uf_resolve_word(p, f, y, xw, W32);
-  }
-  if (changed) atomicExch(p.flags + 4, 1);
-  __threadfence();
-  B2C_GRID_SYNC();
-
-  B2C_STAMP(4);
-  // ---- E: S plane -> u8 {0,255} ----
-  if (p.edges && !p.skip_expand) {
-    const int gpr = (p.w + 15) >> 4;
-    for (int row_ = gwarp; row_ < nrows; row_ += nwarps)
-      for (int g = lane, f = row_ / p.h, y = row_ - f * p.h; g < gpr; g += 32) {
-      const uint32_t word = __ldcg(p.S + f * p.plane_frame_stride + (long long)y * p.plane_pitch + (g >> 1));
-      const uint32_t bits = (word >> ((g & 1) * 16)) & 0xFFFFu;
-      uint8_t *out = p.edges + f * p.edges_frame_stride + (long long)y * p.edges_pitch + g * 16;
-      const int n = min(16, p.w - g * 16);
-      if (n == 16 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
-        uint4 v;
-        v.x = (((bits & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
-        v.y = ((((bits >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
-        v.z = ((((bits >> 8) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
-        v.w = ((((bits >> 12) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
-        *reinterpret_cast<uint4 *>(out) = v;
-      } else {
-        for (int k = 0; k < n; ++k) out[k] = ((bits >> k) & 1u) ? 255 : 0;
-      }
-    }
-  }
-  B2C_STAMP(5);
-#undef B2C_FOR_WORDS
-}
-
 // =====================================================================================================================
-// The same union-find as FOUR ordinary launches on one stream (no host round trip between them):
-//   k_uf_tile (planes + tile-local union-find in shared memory) -> k_uf_border -> k_uf_resolve -> k_uf_expand.
-// Kernel boundaries replace the grid-wide barriers and fences of the cooperative version, every phase gets its own
-// thread mapping (one thread per plane word; words without weak pixels leave at once) and the block scheduler
-// balances the load.  No work list and no counter: a same-address atomic per warp (list append, "changed" flag) cost
-// more than the phases themselves (measured 50-95 us per 32 frames).
+// THREE ordinary launches on one stream (no host round trip between them):
+//   k_uf_tile (tile-local union-find in shared memory) -> k_uf_border -> k_uf_resolve (+ expansion to the u8 map).
+// Kernel boundaries take the place of grid-wide barriers, every phase gets its own thread mapping (one thread per
+// plane word; words without weak pixels leave at once) and the block scheduler balances the load.
 // =====================================================================================================================
 constexpr int UFK_THREADS = 256;
+constexpr int UF_XW_BITS = 12;   // border-list entry = (row << 12) | plane word: images up to 131072 pixels wide, 2^20 rows
 
 // ---- tile build: the union-find of a 32-row x 256-pixel tile entirely in shared memory ------------------------------
 // Concurrent unions on a long weak line build a parent chain as long as the line (every run hooks under the run above
@@ -352,14 +173,10 @@ __global__ void __launch_bounds__(UT_THREADS) k_uf_tile(const B2cHystParams p, u
   {   // ---- phase 0, one thread per plane word: S / C planes, tile copies, compaction of the words with weak pixels
     const int ly = tid >> 3, lw = tid & 7, y = y0 + ly, xw = xw0 + lw;
     uint32_t wd = 0u, sM = 0u;
-    if (y < p.h && xw < wpr) {
+    if (y < p.h && xw < wpr) {   // the planes were written by the stencil kernel: S = strong, C = weak | strong
       const long long o = f * p.plane_frame_stride + (long long)y * p.plane_pitch + xw;
-      const uint32_t *mrow = p.map2 + f * p.map_frame_stride + (long long)y * p.map_pitch;
-      const uint32_t m0 = mrow[2 * xw], m1 = (2 * xw + 1 < p.map_pitch) ? mrow[2 * xw + 1] : 0u;
-      sM = (m0 & 0xFFFFu) | (m1 << 16);
-      wd = (m0 >> 16) | (m1 & 0xFFFF0000u);
-      p.S[o] = sM;
-      p.C[o] = sM | wd;
+      sM = p.S[o];
+      wd = p.C[o] & ~sM;
     }
     LW[tid] = wd;
     LS[tid] = sM;
@@ -391,19 +208,15 @@ __global__ void __launch_bounds__(UT_THREADS) k_uf_tile(const B2cHystParams p, u
   const uint32_t wd = act ? LW[t] : 0u;
   const int lbase = 1 + t * 16;   // local node of the first run of this word
   if (act) {
-    // strong bits of the 3x3 neighbourhood, on words: from the tile copy, or from global memory outside the tile.
-    // Rows -1 and h are the ghost rows of the S plane; inside the frame the words are rebuilt from the map (the S
-    // words of other tiles may not have been written yet).
+    // strong bits of the 3x3 neighbourhood, on words: from the tile copy, or from the S plane outside the tile (rows -1
+    // and h are the zero ghost rows of the plane)
     const int pp = p.plane_pitch;
     const uint32_t *Sr = p.S + f * p.plane_frame_stride + (long long)y * pp + xw;
     auto srow = [&](int dy, int dx) -> uint32_t {   // S word (y + dy, xw + dx)
       const int l2 = ly + dy, w2 = lw + dx, x2 = xw + dx, yy = y + dy;
       if (x2 < 0 || x2 >= wpr) return 0u;
-      if (l2 >= 0 && l2 < UT_ROWS && yy < p.h && w2 >= 0 && w2 < UT_WORDS) return LS[l2 * UT_WORDS + w2];   // (row h is a ghost row: global)
-      if (yy < 0 || yy >= p.h) return __ldcg(Sr + (long long)dy * pp + dx);
-      const uint32_t *mr = p.map2 + f * p.map_frame_stride + (long long)yy * p.map_pitch;
-      const uint32_t a = mr[2 * x2], b = (2 * x2 + 1 < p.map_pitch) ? mr[2 * x2 + 1] : 0u;
-      return (a & 0xFFFFu) | (b << 16);
+      if (l2 >= 0 && l2 < UT_ROWS && yy < p.h && w2 >= 0 && w2 < UT_WORDS) return LS[l2 * UT_WORDS + w2];
+      return __ldg(Sr + (long long)dy * pp + dx);
     };
     uint32_t v = LS[t] | srow(-1, 0) | srow(1, 0), vl = 0u, vr = 0u;
     if (wd & 1u) vl = srow(-1, -1) | srow(0, -1) | srow(1, -1);
@@ -427,7 +240,7 @@ __global__ void __launch_bounds__(UT_THREADS) k_uf_tile(const B2cHystParams p, u
       int base = 0;
       if (lane == leader) base = atomicAdd(bcount + f, __popc(bm));
       base = __shfl_sync(B2C_FULL, base, leader);
-      if (bw) blist[(long long)f * bcap + base + __popc(bm & ((1u << lane) - 1u))] = ((uint32_t)y << 10) | (uint32_t)xw;
+      if (bw) blist[(long long)f * bcap + base + __popc(bm & ((1u << lane) - 1u))] = ((uint32_t)y << UF_XW_BITS) | (uint32_t)xw;
     }
   }
   __syncthreads();
@@ -495,45 +308,10 @@ __global__ void __launch_bounds__(UFK_THREADS) k_uf_border(const B2cHystParams p
   const int f = blockIdx.z, n = 4 * bcount[f], W32 = p.plane_pitch * 32;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t e = blist[(long long)f * bcap + (i >> 2)];
-    const int kind = i & 3, y = (int)(e >> 10), xw = (int)(e & 1023u);
+    const int kind = i & 3, y = (int)(e >> UF_XW_BITS), xw = (int)(e & ((1u << UF_XW_BITS) - 1u));
     const bool top = (y % UT_ROWS) == 0, left = (xw % UT_WORDS) == 0, right = (xw % UT_WORDS) == UT_WORDS - 1;
     const bool doW = kind == 0 && left, doN = kind == 1 && top, doNW = kind == 2 && (top || left), doNE = kind == 3 && (top || right);
     if (doW || doN || doNW || doNE) uf_union_word(p, f, y, xw, W32, doW, doN, doNW, doNE);
-  }
-}
-
-// Row-band mode, rounds after the first: the planes and the union-find forest of the band are still valid (a run is
-// promoted as a whole or not at all), only the ghost rows have gained strong bits.  Every weak run of the first / last
-// band row that touches one of them hangs its root under node 0; k_uf_resolve then promotes the components.
-// Grid: x = blocks of words, y = 0 (first row, ghost row -1) / 1 (last row, ghost row h).
-__global__ void __launch_bounds__(UFK_THREADS) k_uf_seed(const B2cHystParams p)
-{
-  const int wpr = (p.w + 31) >> 5, W32 = p.plane_pitch * 32, pp = p.plane_pitch;
-  const int xw = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.z;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) { p.flags[3] += 1; p.flags[4] = 0; }   // flags[6] ("a new seed arrived") is cleared by the host side before the launch
-  if (xw >= wpr) return;
-  const int y = blockIdx.y ? p.h - 1 : 0, yg = blockIdx.y ? p.h : -1;
-  const long long o = f * p.plane_frame_stride + (long long)y * pp + xw;
-  const uint32_t wd = p.C[o] & ~p.S[o];
-  if (wd == 0u) return;
-  const uint32_t *G = p.S + f * p.plane_frame_stride + (long long)yg * pp + xw;
-  const uint32_t g = __ldcg(G), gl = xw > 0 ? __ldcg(G - 1) : 0u, gr = xw + 1 < wpr ? __ldcg(G + 1) : 0u;
-  const uint32_t near = wd & (g | (g << 1) | (g >> 1) | (gl >> 31) | (gr << 31));
-  if (near == 0u) return;
-  int *P = p.parent + f * p.parent_frame_stride;
-  const int base = y * W32 + xw * 32 + 1;
-  uint32_t m = wd;
-  while (m) {
-    const uint32_t lo = m & (0u - m);
-    const uint32_t run = m & ~(m + lo);
-    m &= ~run;
-    if (run & near) {
-      const int r = uf_find(P, base + __ffs((int)lo) - 1);
-      if (r != 0) {
-        atomicMin(P + r - 1, 0);
-        if (__ldcg(p.flags + 6) == 0) __stcg(p.flags + 6, 1);   // this band has something new to resolve (and maybe to pass on)
-      }
-    }
   }
 }
 
@@ -558,10 +336,10 @@ __device__ __forceinline__ bool uf_resolve_expand_word_sc(const B2cHystParams &p
     }
     if (add) {
       s |= add;
-      p.S[o] = s;
       changed = true;
     }
   }
+  if (!ONLY_CHANGED || changed) p.E[o] = s;   // E = edges: strong | promoted weak (S itself stays what the stencil wrote)
   if (EXPAND && (!ONLY_CHANGED || changed)) {   // (ONLY_CHANGED: the map already holds the previous state of every word)
     uint8_t *out = p.edges + f * p.edges_frame_stride + (long long)y * p.edges_pitch + xw * 32;
     const int n = min(32, p.w - xw * 32);
@@ -586,12 +364,12 @@ template <bool EXPAND, bool ONLY_CHANGED = false>
 __device__ __forceinline__ bool uf_resolve_expand_word(const B2cHystParams &p, int f, int y, int xw, int W32)
 {
   const long long o = f * p.plane_frame_stride + (long long)y * p.plane_pitch + xw;
-  return uf_resolve_expand_word_sc<EXPAND, ONLY_CHANGED>(p, f, y, xw, W32, p.S[o], p.C[o]);
+  return uf_resolve_expand_word_sc<EXPAND, ONLY_CHANGED>(p, f, y, xw, W32, (ONLY_CHANGED ? p.E : p.S)[o], p.C[o]);
 }
 
 // One thread per plane word of TWO rows (both rows' loads in flight before either is looked at): block =
 // (blockDim.x words) x (2 * blockDim.y rows); grid: x = word blocks of a row, y = row blocks, z = frame.
-template <bool EXPAND>
+template <bool EXPAND, bool ONLY_CHANGED = false>
 __global__ void __launch_bounds__(UFK_THREADS) k_uf_resolve(const B2cHystParams p, int *bcount)
 {
   if ((p.skip && __ldcg(p.skip)) || (p.need && __ldcg(p.need) == 0)) return;
@@ -602,9 +380,10 @@ __global__ void __launch_bounds__(UFK_THREADS) k_uf_resolve(const B2cHystParams 
   if (xw < wpr && y < p.h) {
     const long long o = f * p.plane_frame_stride + (long long)y * p.plane_pitch + xw;
     const bool two = y + 1 < p.h;
-    const uint32_t s0 = p.S[o], c0 = p.C[o], s1 = two ? p.S[o + p.plane_pitch] : 0u, c1 = two ? p.C[o + p.plane_pitch] : 0u;
-    changed = uf_resolve_expand_word_sc<EXPAND>(p, f, y, xw, W32, s0, c0);
-    if (two) changed |= uf_resolve_expand_word_sc<EXPAND>(p, f, y + 1, xw, W32, s1, c1);
+    const uint32_t *cur = ONLY_CHANGED ? p.E : p.S;   // first pass: from the stencil's S plane; re-pass (row bands): from the edges so far
+    const uint32_t s0 = cur[o], c0 = p.C[o], s1 = two ? cur[o + p.plane_pitch] : 0u, c1 = two ? p.C[o + p.plane_pitch] : 0u;
+    changed = uf_resolve_expand_word_sc<EXPAND, ONLY_CHANGED>(p, f, y, xw, W32, s0, c0);
+    if (two) changed |= uf_resolve_expand_word_sc<EXPAND, ONLY_CHANGED>(p, f, y + 1, xw, W32, s1, c1);
   }
   // a plain store, and only while the flag is still clear (a same-address atomic per thread serialises in L2 and cost
   // more than the whole phase)
@@ -618,7 +397,7 @@ __global__ void __launch_bounds__(UFK_THREADS) k_uf_expand(const B2cHystParams p
   const long long total = (long long)p.nframes * p.h * gpr;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int row_ = (int)(i / gpr), g = (int)(i - (long long)row_ * gpr), f = row_ / p.h, y = row_ - f * p.h;
-    const uint32_t word = p.S[f * p.plane_frame_stride + (long long)y * p.plane_pitch + (g >> 1)];
+    const uint32_t word = p.E[f * p.plane_frame_stride + (long long)y * p.plane_pitch + (g >> 1)];
     const uint32_t bits = (word >> ((g & 1) * 16)) & 0xFFFFu;
     uint8_t *out = p.edges + f * p.edges_frame_stride + (long long)y * p.edges_pitch + g * 16;
     const int n = min(16, p.w - g * 16);

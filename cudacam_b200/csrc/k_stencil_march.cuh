@@ -1,4 +1,4 @@
-// k_stencil_march.cuh -- the throughput kernel: BGR8 -> 2-bit weak/strong map in ONE launch.
+// k_stencil_march.cuh -- the throughput kernel: BGR8 -> 2-bit weak/strong map (as the bit planes S and C) in ONE launch.
 //
 // Replaces six launches of the reference (rgb2mono, gaussianFilter5x5, sobelXY, gradSlope, nonMaxSuppr,
 // doubleThreshold: src/cvp/cannyEdgeD.cu:53-293, launched at src/cvp/cannyEdgeH.cu:214-295) and their 22 B/pixel of
@@ -614,11 +614,9 @@ __device__ __forceinline__ void m_c_row(const B2cStencilParams &p, const MarchGe
         if (flag_even) list[n0 + __popc(m1 & lt_mask)] = (uint16_t)(0x100u | lane);
         __syncwarp();
         if (!(B2C_X & 32)) {
-          // few entries (the usual case): one pass of 2 per lane; crowded pairs of rows (a horizontal edge fills all
-          // 30 groups of a row): 4 per lane, so that 16 dependency chains are in flight per pass instead of 8
-          if (cnt <= 8) m_nms_pass<K, 2>(p, smem, list, cnt, 0, rr, sflip);
-          else
-            for (int q0 = 0; q0 < cnt; q0 += 16) m_nms_pass<K, 4>(p, smem, list, cnt, q0, rr, sflip);
+          // 8 entries per pass, 2 per lane: both dependency chains of a lane are in flight together.  (4 per lane was
+          // measured: 128 registers, 58 KB of code, 1.4x slower.)
+          for (int q0 = 0; q0 < cnt; q0 += 8) m_nms_pass<K, 2>(p, smem, list, cnt, q0, rr, sflip);
         }
         __syncwarp();
       }
@@ -670,15 +668,19 @@ __device__ __forceinline__ void m_c_block(const B2cStencilParams &p, const March
     // out tile: 64 bytes per row = 32 strong bytes (one per 8-pixel group, byte g = output columns 8g .. 8g+7) + 32 weak
     {
       const int wi = lane & 15, gw = blockIdx.x * (MT_X / 16) + wi;
-      uint32_t *dst = p.map2 + (long long)g.frame * p.map_frame_stride + (long long)g.Y0 * p.map_pitch + gw;
+      const long long o0 = (long long)g.frame * p.pl_frame_stride16 + (long long)g.Y0 * p.pl_pitch16 + gw;
       uint16_t *s16 = reinterpret_cast<uint16_t *>(smem + MS_OUT);
+      const int gmax = (p.w + 15) >> 4;   // 16-pixel groups per row
 #pragma unroll
       for (int it = 0; it < MK / 2; ++it) {
         const int idx = 2 * it + (lane >> 4), n = b0 - 2 + idx;
-        const uint32_t v = (uint32_t)s16[idx * 32 + wi] | ((uint32_t)s16[idx * 32 + 16 + wi] << 16);
+        const uint32_t sv = s16[idx * 32 + wi], wv = s16[idx * 32 + 16 + wi];
         s16[idx * 32 + wi] = 0;
         s16[idx * 32 + 16 + wi] = 0;
-        if (wi < MT_X / 16 && gw < p.map_pitch && n >= 0 && n < g.rows_out) dst[(long long)n * p.map_pitch] = v;
+        if (wi < MT_X / 16 && gw < gmax && n >= 0 && n < g.rows_out) {   // the two planes ARE the 2-bit map: S = strong, C = weak | strong
+          p.pl_S[o0 + (long long)n * p.pl_pitch16] = (uint16_t)sv;
+          p.pl_C[o0 + (long long)n * p.pl_pitch16] = (uint16_t)(sv | wv);
+        }
       }
       __syncwarp();
     }

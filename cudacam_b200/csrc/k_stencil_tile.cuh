@@ -126,7 +126,10 @@ __global__ void __launch_bounds__(TILE_THREADS) k_stencil_tile(const B2cStencilP
     const unsigned bs = __ballot_sync(B2C_FULL, strong), bw = __ballot_sync(B2C_FULL, weak);
     if ((lane & 15) == 0 && valid) {
       const unsigned sh = lane & 16;
-      p.map2[(long long)frame * p.map_frame_stride + (long long)y * p.map_pitch + (x >> 4)] = ((bs >> sh) & 0xFFFFu) | (((bw >> sh) & 0xFFFFu) << 16);
+      const long long o = (long long)frame * p.pl_frame_stride16 + (long long)y * p.pl_pitch16 + (x >> 4);
+      const unsigned s16 = (bs >> sh) & 0xFFFFu, w16 = (bw >> sh) & 0xFFFFu;
+      p.pl_S[o] = (uint16_t)s16;
+      p.pl_C[o] = (uint16_t)(s16 | w16);
     }
     if (EMIT && valid && frame == 0) {
       if (p.mono) p.mono[(long long)y * p.pitch8 + x] = s_mono[(r + 4) * MW + c + 4];

@@ -53,7 +53,7 @@ enum {
   B2C_BUF_NMS = 3,    /* u8  w*h   == d_nms    (:76)                                       */
   B2C_BUF_THRESH = 4, /* u8  w*h   == d_thresh (:79) {0,128,255}                           */
   B2C_BUF_EDGES = 5,  /* u8  w*h   == d_hyster after removeCandidates (:84) {0,255}        */
-  B2C_BUF_MAP2 = 6,   /* u32 per 16 px: bits 0-15 strong, 16-31 weak (the 2-bit map)       */
+  B2C_BUF_MAP2 = 6,   /* u32 per 16 px: bits 0-15 strong, 16-31 weak (view of the 2-bit map) */
   B2C_BUF_BITS = 7,   /* u32 per 32 px: final edges, 1 bit per pixel                       */
   B2C_BUF_VIEW = 8    /* u8  w*h tight: what the reference copies into its GL PBO
                          (cannyEdgeH.cu:154-212) for the stage passed to the last b2c_run  */
@@ -75,7 +75,7 @@ B2C_API int b2c_get_high_threshold(b2c_handle h);
 /* ---- profiling toggle: enableKernelProfiling / isKernelProfilingEnabled (cannyEdgeH.hpp:31-32).
  * Timings are recorded with events and only read back by b2c_last_timings (no sync in the hot path,
  * unlike cannyEdgeH.cu:415-430).  ms[0]=upload, [1]=fused stencil, [2]=hysteresis, [3]=output, [4]=total,
- * [5]=hysteresis rounds used (count, not ms). */
+ * [5]=0 (was: hysteresis rounds; the union-find needs none). */
 B2C_API int b2c_enable_profiling(b2c_handle h, int on);
 B2C_API int b2c_is_profiling_enabled(b2c_handle h);
 B2C_API int b2c_last_timings(b2c_handle h, float *ms, int n);
@@ -95,6 +95,10 @@ B2C_API int b2c_run_device(b2c_handle h, const uint8_t *dev_bgr, size_t row_stri
 /* the two halves of b2c_run_device, separately (bench / profiling of the fused stencil alone) */
 B2C_API int b2c_stencil_device(b2c_handle h, const uint8_t *dev_bgr, size_t row_stride, size_t frame_stride, int n, void *stream);
 B2C_API int b2c_hysteresis_device(b2c_handle h, int n, uint8_t *dev_edges, size_t edges_pitch, size_t edges_frame_stride, void *stream);
+/* hysteresis on a map produced elsewhere: a thresholded image (0 / 128 / 255 = the reference's d_threshImage,
+ * cannyEdgeD.cu:274-292) from HOST memory becomes frame 0's state in place of a stencil run; follow with
+ * b2c_hysteresis_device(h, 1, ...) or, on a band handle, b2c_band_hysteresis.  Blocking. */
+B2C_API int b2c_load_thresh(b2c_handle h, const uint8_t *host_thresh, size_t row_stride);
 
 /* ---- batch of host frames through the pinned, double-buffered async pipeline (H2D / kernels / D2H
  * overlapped on separate streams).  frames = n contiguous frames of row_stride*height bytes;
@@ -122,43 +126,46 @@ B2C_API int b2c_host_free(void *host_ptr);
 B2C_API void *b2c_stream(b2c_handle h);
 
 /* ---- row-band mode for one image split over several GPUs (BASELINE config 5; no reference counterpart).
- * The band covers global rows [y0, y0+band_rows) of a height_global image.  Input passed to
- * b2c_band_stencil points at the band's first row inside a buffer that also holds the 4 rows above it
- * (unless the band starts at global row 0) and the 4 rows below it (unless it ends at the last global row): the stencil needs 2 (Gaussian) + 1 (Sobel) + 1 (NMS) neighbour rows, and uses the
- * reference's zero padding only outside the global image. */
+ * The band covers global rows [y0, y0+band_rows) of a height_global image (a band with a neighbour has >= 4 rows).
+ * Input passed to b2c_band_stencil points at the band's first row inside a buffer that also holds the 4 rows above it
+ * (unless the band starts at global row 0) and the 4 rows below it (unless it ends at the last global row): the
+ * stencil needs 2 (Gaussian) + 1 (Sobel) + 1 (NMS) neighbour rows, and uses the reference's zero padding only outside
+ * the global image.  Per image: [halo exchange] -> b2c_band_stencil -> b2c_band_hysteresis (band-local fixpoint, planes
+ * and union-find forest are kept) -> ONE exchange of seam records -> solve; the result equals the unsharded run bit
+ * for bit.  All calls are asynchronous on `stream`. */
 B2C_API int b2c_create_band(b2c_handle *out, int device, int width, int band_rows, int y0, int height_global);
 B2C_API int b2c_band_stencil(b2c_handle h, const uint8_t *dev_bgr_band_row0, size_t row_stride, void *stream);
-/* Band-local hysteresis to a fixpoint given the current ghost rows.  first_call != 0: planes and union-find forest
- * from the 2-bit map (3 launches); first_call == 0: re-entry -- the forest is kept, the weak runs of the first / last
- * row that touch a strong ghost pixel are seeded and the components resolved (2 launches).  write_edges: 0 = bit plane
- * only, 1 = also expand to the u8 edge map, 2 = ONLY expand the (final) bit plane.  *changed (may be null; a non-null
- * pointer makes the call blocking) = 1 if any edge bit was added. */
-B2C_API int b2c_band_hysteresis(b2c_handle h, int first_call, int write_edges, int *changed, void *stream);
-/* boundary rows of the S plane: which = 0 first band row, 1 last band row (to send);
- * ghost rows: which = 0 row above the band, 1 row below (to receive).  words = ceil(w/32). */
-B2C_API int b2c_band_boundary_ptr(b2c_handle h, int which, void **dev_ptr, int *words);
-B2C_API int b2c_band_ghost_ptr(b2c_handle h, int which, void **dev_ptr, int *words);
-/* device int that is 1 after a re-entry call of b2c_band_hysteresis if a ghost row seeded anything new in this band
- * (cleared at the start of every re-entry call); the row-band driver all-reduces it to detect the global fixpoint */
-B2C_API int b2c_band_flag_ptr(b2c_handle h, void **dev_ptr);
+B2C_API int b2c_band_hysteresis(b2c_handle h, void *stream);
+/* Cross-band hysteresis in one step.  Every band publishes its SEAM RECORD (b2c_band_seam_bytes bytes: the edge and
+ * unresolved-weak bit rows of its first and last row + a component label per unresolved run), the caller all-gathers
+ * the records of all bands in band order (any transport: NCCL, MPI, a memcpy), and every band solves the same small
+ * connected-components problem over all seams and promotes its own components that reach an edge pixel of any band.
+ * b2c_band_seam_publish: *record_dev = device address of this band's record (owned by the handle);
+ * b2c_band_seam_solve: all_records_dev = world records, b2c_band_seam_bytes apart. */
+B2C_API int b2c_band_seam_bytes(b2c_handle h, size_t *bytes);
+B2C_API int b2c_band_seam_publish(b2c_handle h, void **record_dev, void *stream);
+B2C_API int b2c_band_seam_solve(b2c_handle h, const void *all_records_dev, int world, int rank, void *stream);
+/* blocking: weak runs of this band promoted by the last solve, and whether a peer-to-peer wait timed out */
+B2C_API int b2c_band_status(b2c_handle h, int *promoted_runs, int *error);
 
-/* Peer-to-peer rounds for ranks of ONE box (one process per GPU): instead of NCCL send/recv + all-reduce per round, every
- * rank maps the other ranks' mailboxes (CUDA IPC) and the rounds run on the device: boundary rows and "seeded" flags
- * are stored straight into the peers' memory over NVLink, convergence is decided by every rank from the same flags.
- * b2c_band_p2p_export: 144-byte blob (IPC handles of this band's mailbox and input buffer + its height), to be
- * all-gathered by the caller; b2c_band_p2p_open: the blobs of all ranks, in rank order;
- * b2c_band_p2p_converge: after the first b2c_band_hysteresis call -- runs exchange / seed / resolve rounds until the
- * global fixpoint, reading the device-side done flag once per `rounds_per_sync` rounds; blocking; *rounds_out =
- * exchange rounds executed.  Follow with b2c_band_hysteresis(h, 0, 2, ...) to expand the final bit plane. */
+/* Peer-to-peer transport for ranks of ONE box: every rank maps the other ranks' mailboxes and band input buffers
+ * (CUDA IPC between processes: export a 144-byte blob, all-gather the blobs, open; or b2c_band_p2p_open_local for
+ * bands of one process) and the halo rows and seam records travel as ordinary stores over NVLink, with flag words
+ * instead of collectives.
+ * b2c_band_input: the band's input buffer owned by the handle (so that it can be shared): rows 0..3 = halo rows above
+ * the band, rows 4..4+band_rows-1 = the band, then 4 halo rows; rows are row_stride bytes apart;
+ * b2c_band_p2p_halo: my first / last 4 rows -> the neighbours' buffers; later work on `stream` sees both neighbours' rows;
+ * b2c_band_p2p_seam: publish + all-gather over peer memory + solve (replaces the publish / gather / solve calls above).
+ * phase: B2C_P2P_ALL for a rank that drives one band.  A process that drives SEVERAL bands (b2c_band_p2p_open_local)
+ * gives every band its own stream and calls B2C_P2P_PUSH for all bands before B2C_P2P_WAIT for any: the waits spin on the
+ * device and must never be queued ahead of the stores they wait for.  Every wait has a 2 s time-out (b2c_band_status). */
+enum { B2C_P2P_ALL = 0, B2C_P2P_PUSH = 1, B2C_P2P_WAIT = 2 };
+B2C_API int b2c_band_input(b2c_handle h, void **dev_ptr, size_t *row_stride);
 B2C_API int b2c_band_p2p_export(b2c_handle h, void *blob_144);
 B2C_API int b2c_band_p2p_open(b2c_handle h, const void *all_blobs, int world, int rank);
-/* the band's input buffer owned by the handle (so that it can be shared with the neighbours): row 0..3 = halo rows
- * above the band, rows 4..4+band_rows-1 = the band, then 4 halo rows; rows are row_stride bytes apart */
-B2C_API int b2c_band_input(b2c_handle h, void **dev_ptr, size_t *row_stride);
-/* input halo exchange over peer memory: my first / last 4 rows -> the neighbours' buffers; asynchronous on `stream`,
- * later work on the stream sees both neighbours' rows */
-B2C_API int b2c_band_p2p_halo(b2c_handle h, void *stream);
-B2C_API int b2c_band_p2p_converge(b2c_handle h, int rounds_per_sync, int *rounds_out, void *stream);
+B2C_API int b2c_band_p2p_open_local(b2c_handle h, const b2c_handle *all_handles, int world, int rank);
+B2C_API int b2c_band_p2p_halo(b2c_handle h, void *stream, int phase);
+B2C_API int b2c_band_p2p_seam(b2c_handle h, void *stream, int phase);
 
 /* ---- misc */
 B2C_API const char *b2c_strerror(int status);
@@ -167,11 +174,11 @@ B2C_API const char *b2c_version(void);
 B2C_API int b2c_device_count(void);
 /* kernels launched by this handle since creation (bench.py reports it as gpu_launches) */
 B2C_API long long b2c_launch_count(b2c_handle h);
-/* options: "stencil_impl" 0 = marching warp-per-strip kernel (default), 1 = staged tile kernel (all-stages path),
- * 2 = fused CTA-tile kernel; "hyst_impl" 0 = union-find (default), 1 = tile rounds; "hyst_max_rounds" */
+/* options: "stencil_impl" 0 = marching kernel (default), 1 = staged tile kernel (the all-stages path of the
+ * accessors); "march_rb" rows per band of the marching kernel (0 = automatic); "hyst_phase_timing"; "uf_spread" */
 B2C_API int b2c_set_option(b2c_handle h, const char *name, int value);
-/* read-only facts: "hyst_rounds" (rounds used by the last b2c_run), "hyst_grid", "sm_count", "stencil_impl",
- * "in_row_stride", "plane_pitch_words", "map_pitch_words" */
+/* read-only facts: "sm_count", "stencil_impl", "march_ctas_per_sm", "march_band_rows", "in_row_stride",
+ * "plane_pitch_words", "map_pitch_words", "hyst_phase_us0..2" */
 B2C_API int b2c_get_info(b2c_handle h, const char *name);
 
 /* ---- deterministic synthetic frames (host side; identical to cudacam_b200/synth.py).

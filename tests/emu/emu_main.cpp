@@ -5,8 +5,8 @@
 #include "cuda_emu.h"
 
 #include "../../cudacam_b200/csrc/b2c_device.cuh"
-#include "../../cudacam_b200/csrc/k_hysteresis.cuh"
 #include "../../cudacam_b200/csrc/k_hysteresis_uf.cuh"
+#include "../../cudacam_b200/csrc/k_band_seam.cuh"
 #include "../../cudacam_b200/csrc/k_stencil_tile.cuh"
 #ifdef B2C_EMU_FUSED
 #include "../../cudacam_b200/csrc/k_stencil_march.cuh"
@@ -35,7 +35,18 @@ __attribute__((visibility("default"))) int emu_stencil(int impl, const uint8_t *
   p.zeros = zeros;
   p.bgr = bgr; p.row_stride = row_stride; p.frame_stride = frame_stride;
   p.w = w; p.h = h; p.y0 = y0; p.h_glob = h_glob; p.nframes = nframes; p.channels = g_emu_channels;
-  p.map2 = map2; p.map_pitch = (w + 15) / 16; p.map_frame_stride = (long long)h * p.map_pitch;
+  // the kernels write the bit planes S and C; the tests look at the 2-bit map view
+  const int gpr = (w + 15) / 16, pitch16 = ((w + 31) / 32 + 3) / 4 * 4 * 2;
+  std::vector<uint16_t> pS((size_t)nframes * h * pitch16, 0), pC((size_t)nframes * h * pitch16, 0);
+  p.pl_S = pS.data(); p.pl_C = pC.data(); p.pl_pitch16 = pitch16; p.pl_frame_stride16 = (long long)h * pitch16;
+  auto to_map2 = [&] {
+    for (int f = 0; f < nframes; ++f)
+      for (int y = 0; y < h; ++y)
+        for (int g = 0; g < gpr; ++g) {
+          const uint32_t sv = pS[((size_t)f * h + y) * pitch16 + g], cv = pC[((size_t)f * h + y) * pitch16 + g];
+          map2[((size_t)f * h + y) * gpr + g] = sv | ((cv & ~sv) << 16);
+        }
+  };
   p.lo = lo; p.hi = hi;
   fill_gk(p.gk);
   b2c_fill_thresholds(p);
@@ -47,77 +58,170 @@ __attribute__((visibility("default"))) int emu_stencil(int impl, const uint8_t *
       emu::launch(grid, dim3(b2c::TILE_THREADS), b2c::TILE_SMEM, false, [p] { b2c::k_stencil_tile<true>(p); });
     else
       emu::launch(grid, dim3(b2c::TILE_THREADS), b2c::TILE_SMEM, false, [p] { b2c::k_stencil_tile<false>(p); });
+    to_map2();
     return 0;
   }
 #ifdef B2C_EMU_FUSED
-  if (impl >= 100) return b2c::march_emu_launch(p, impl - 100);   // impl = 100 + rows per band
+  if (impl >= 100) {   // impl = 100 + rows per band
+    const int rc = b2c::march_emu_launch(p, impl - 100);
+    to_map2();
+    return rc;
+  }
   return -1;
 #else
   return -1;
 #endif
 }
 
-// S/C planes are allocated here (with ghost rows); ghost_top/ghost_bot (wpr words each, may be null) seed the
-// ghost rows (row-band mode).  Returns rounds used; *changed = flags[4].
-__attribute__((visibility("default"))) int emu_hysteresis(const uint32_t *map2, int w, int h, int nframes, int grid_blocks, int tile_rows, uint8_t *edges, uint32_t *bits_out,
-                                                          const uint32_t *ghost_top, const uint32_t *ghost_bot, int *changed)
+}   // extern "C"
+
+// ---- hysteresis: planes from the 2-bit map (what the stencil kernels write), then the product's three kernels ------
+namespace
 {
-  const int wpr = (w + 31) / 32, pitch = (wpr + 3) / 4 * 4;
-  const long long fs = (long long)(h + 2) * pitch;
-  std::vector<uint32_t> S((size_t)fs * nframes, 0), Cc((size_t)fs * nframes, 0);
-  if (ghost_top) memcpy(S.data(), ghost_top, wpr * 4);
-  if (ghost_bot) memcpy(S.data() + (size_t)(h + 1) * pitch, ghost_bot, wpr * 4);
+struct EmuPlanes {
+  int w = 0, h = 0, n = 0, wpr = 0, pitch = 0;
+  long long fs = 0;
+  std::vector<uint32_t> S, C, E;
+  std::vector<int> parent;
+  std::vector<uint32_t> bl;
+  std::vector<int> bc;
+  int bcap = 0;
   int flags[16] = { 0 };
-  B2cHystParams p;
-  memset(&p, 0, sizeof(p));
-  p.map2 = map2; p.map_pitch = (w + 15) / 16; p.map_frame_stride = (long long)h * p.map_pitch;
-  p.S = S.data() + pitch; p.C = Cc.data() + pitch; p.plane_pitch = pitch; p.plane_frame_stride = fs;
-  p.w = w; p.h = h; p.nframes = nframes;
-  p.edges = edges; p.edges_pitch = w; p.edges_frame_stride = (long long)w * h;
-  p.flags = flags; p.max_rounds = 1 << 20; p.tile_rows = tile_rows; p.spread = 1;
-  std::vector<int> parent((size_t)nframes * h * pitch * 32, -12345);
-  p.parent = parent.data(); p.parent_frame_stride = (long long)h * pitch * 32;
-  if (tile_rows > 0)
-    emu::launch(dim3(grid_blocks), dim3(b2c::HYST_THREADS), b2c::hyst_smem_bytes(tile_rows), true, [p] { b2c::k_hysteresis(p); });
-  else if (tile_rows == 0)   // the cooperative union-find kernel
-    emu::launch(dim3(grid_blocks), dim3(b2c::UF_THREADS), b2c::UF_SMEM, true, [p] { b2c::k_hysteresis_uf(p); });
-  else {   // tile_rows < 0: union-find as four launches; ghost rows given => re-entry on planes built by a first pass
-    const int reps = (ghost_top || ghost_bot) ? 2 : 1;   // second repetition exercises the REENTRY build on the retained planes
-    const dim3 gt((wpr + b2c::UT_WORDS - 1) / b2c::UT_WORDS, (h + b2c::UT_ROWS - 1) / b2c::UT_ROWS, nframes);
-    const int bcap = (int)gt.y * wpr + 2 * (int)gt.x * h;
-    std::vector<uint32_t> bl((size_t)nframes * bcap + 1);
-    std::vector<int> bc(nframes, 0);
+  void init(int w_, int h_, int n_)
+  {
+    w = w_; h = h_; n = n_;
+    wpr = (w + 31) / 32;
+    pitch = (wpr + 3) / 4 * 4;
+    fs = (long long)(h + 2) * pitch;
+    S.assign((size_t)fs * n, 0); C.assign((size_t)fs * n, 0); E.assign((size_t)fs * n, 0);
+    parent.assign((size_t)n * h * pitch * 32, -12345);
+    const int gy = (h + b2c::UT_ROWS - 1) / b2c::UT_ROWS, gx = (wpr + b2c::UT_WORDS - 1) / b2c::UT_WORDS;
+    bcap = gy * wpr + 2 * gx * h;
+    bl.assign((size_t)n * bcap + 1, 0);
+    bc.assign(n, 0);
+  }
+  void from_map2(const uint32_t *map2)
+  {
+    const int gpr = (w + 15) / 16;
+    std::fill(S.begin(), S.end(), 0u); std::fill(C.begin(), C.end(), 0u);
+    for (int f = 0; f < n; ++f)
+      for (int y = 0; y < h; ++y)
+        for (int g = 0; g < gpr; ++g) {
+          const uint32_t m = map2[((size_t)f * h + y) * gpr + g], sv = m & 0xFFFFu, cv = sv | (m >> 16);
+          const size_t o = (size_t)f * fs + (size_t)(y + 1) * pitch + (g >> 1);
+          S[o] |= sv << (16 * (g & 1));
+          C[o] |= cv << (16 * (g & 1));
+        }
+  }
+  B2cHystParams params(uint8_t *edges)
+  {
+    B2cHystParams p;
+    memset(&p, 0, sizeof(p));
+    p.S = S.data() + pitch; p.C = C.data() + pitch; p.E = E.data() + pitch; p.plane_pitch = pitch; p.plane_frame_stride = fs;
+    p.w = w; p.h = h; p.nframes = n;
+    p.edges = edges; p.edges_pitch = w; p.edges_frame_stride = (long long)w * h;
+    p.flags = flags; p.spread = 1;
+    p.parent = parent.data(); p.parent_frame_stride = (long long)h * pitch * 32;
+    return p;
+  }
+  void hysteresis(uint8_t *edges)
+  {
+    const B2cHystParams p = params(edges);
+    const dim3 gt((wpr + b2c::UT_WORDS - 1) / b2c::UT_WORDS, (h + b2c::UT_ROWS - 1) / b2c::UT_ROWS, n);
     uint32_t *blp = bl.data();
     int *bcp = bc.data();
-    for (int rep = 0; rep < reps; ++rep) {
-      if (rep == 0) {
-        // first pass WITHOUT the ghost rows when a re-entry follows (they arrive later in row-band mode)
-        std::vector<uint32_t> keep_top, keep_bot;
-        if (reps == 2) {
-          keep_top.assign(S.begin(), S.begin() + pitch);
-          keep_bot.assign(S.begin() + (size_t)(h + 1) * pitch, S.begin() + (size_t)(h + 2) * pitch);
-          std::fill(S.begin(), S.begin() + pitch, 0u);
-          std::fill(S.begin() + (size_t)(h + 1) * pitch, S.begin() + (size_t)(h + 2) * pitch, 0u);
-        }
-        emu::launch(gt, dim3(b2c::UT_THREADS), b2c::UT_SMEM, false, [=] { b2c::k_uf_tile(p, blp, bcp, bcap); });
-        emu::launch(dim3(2, 1, nframes), dim3(b2c::UFK_THREADS), 0, false, [=] { b2c::k_uf_border(p, blp, bcp, bcap); });
-        if (reps == 2) {
-          std::copy(keep_top.begin(), keep_top.end(), S.begin());
-          std::copy(keep_bot.begin(), keep_bot.end(), S.begin() + (size_t)(h + 1) * pitch);
-        }
-      } else {
-        emu::launch(dim3((wpr + b2c::UFK_THREADS - 1) / b2c::UFK_THREADS, 2, nframes), dim3(b2c::UFK_THREADS), 0, false, [=] { b2c::k_uf_seed(p); });
-      }
-      const int tx = 32, ty = 4;
-      const dim3 gr((wpr + tx - 1) / tx, (h + 2 * ty - 1) / (2 * ty), nframes), br(tx, ty);   // a thread takes 2 rows
-      if (rep + 1 < reps) emu::launch(gr, br, 0, false, [=] { b2c::k_uf_resolve<false>(p, bcp); });
-      else emu::launch(gr, br, 0, false, [=] { b2c::k_uf_resolve<true>(p, bcp); });
-    }
+    const int cap = bcap;
+    emu::launch(gt, dim3(b2c::UT_THREADS), b2c::UT_SMEM, false, [=] { b2c::k_uf_tile(p, blp, bcp, cap); });
+    emu::launch(dim3(2, 1, n), dim3(b2c::UFK_THREADS), 0, false, [=] { b2c::k_uf_border(p, blp, bcp, cap); });
+    const int tx = 32, ty = 4;
+    const dim3 gr((wpr + tx - 1) / tx, (h + 2 * ty - 1) / (2 * ty), n), br(tx, ty);   // a thread takes 2 rows
+    if (edges) emu::launch(gr, br, 0, false, [=] { b2c::k_uf_resolve<true>(p, bcp); });
+    else emu::launch(gr, br, 0, false, [=] { b2c::k_uf_resolve<false>(p, bcp); });
   }
+};
+}// namespace
+
+extern "C" {
+// planes from a 2-bit map, then the product's three hysteresis launches; edges may be null (bit plane only)
+__attribute__((visibility("default"))) int emu_hysteresis(const uint32_t *map2, int w, int h, int nframes, uint8_t *edges, uint32_t *bits_out)
+{
+  EmuPlanes P;
+  P.init(w, h, nframes);
+  P.from_map2(map2);
+  P.hysteresis(edges);
   if (bits_out)
     for (int f = 0; f < nframes; ++f)
-      for (int y = 0; y < h; ++y) memcpy(bits_out + ((size_t)f * h + y) * wpr, p.S + f * fs + (long long)y * pitch, wpr * 4);
-  if (changed) *changed = flags[4];
-  return flags[3];
+      for (int y = 0; y < h; ++y) memcpy(bits_out + ((size_t)f * h + y) * P.wpr, P.E.data() + f * P.fs + (long long)(y + 1) * P.pitch, P.wpr * 4);
+  return 0;
+}
+
+// ---- one row band with retained planes and forest (row-band protocol on the CPU) ---------------------------------------
+struct EmuBand {
+  EmuPlanes P;
+  std::vector<uint8_t> edges;
+  std::vector<int> roots, hkey, hval, sP, pre;
+  int ctl[8] = { 0 };
+  int run = 0;
+};
+__attribute__((visibility("default"))) void *emu_band_create(int w, int h)
+{
+  EmuBand *b = new EmuBand;
+  b->P.init(w, h, 1);
+  b->edges.assign((size_t)w * h, 0);
+  const int cap = b2c::seam_cap(b->P.wpr), hs = b2c::seam_hash_size(b->P.wpr);
+  b->roots.assign(2 * cap, 0);
+  b->hkey.assign(hs, 0);
+  b->hval.assign(hs, 0);
+  b->sP.assign((size_t)b2c::SEAM_MAXW * 2 * cap + 1, 0);
+  b->pre.assign((size_t)b2c::SEAM_MAXW * 2 * b->P.wpr, 0);
+  return b;
+}
+__attribute__((visibility("default"))) void emu_band_destroy(void *h) { delete static_cast<EmuBand *>(h); }
+__attribute__((visibility("default"))) int emu_seam_words(int w) { return (int)b2c::seam_rec_words((w + 31) / 32); }
+__attribute__((visibility("default"))) void emu_band_hysteresis(void *h, const uint32_t *map2)
+{
+  EmuBand *b = static_cast<EmuBand *>(h);
+  b->P.from_map2(map2);
+  b->P.hysteresis(b->edges.data());
+}
+static b2c::B2cSeamBand emu_seam_band(EmuBand *b)
+{
+  b2c::B2cSeamBand s;
+  s.S = b->P.E.data() + b->P.pitch; s.C = b->P.C.data() + b->P.pitch;
+  s.plane_pitch = b->P.pitch; s.wpr = b->P.wpr; s.h = b->P.h;
+  s.parent = b->P.parent.data(); s.roots = b->roots.data(); s.hkey = b->hkey.data(); s.hval = b->hval.data();
+  s.hsize = (int)b->hkey.size(); s.ctl = b->ctl;
+  return s;
+}
+constexpr int EMU_SEAM_THREADS = 128;   // (the kernels take the CTA size from blockDim; 1024 OS threads per block would be slow)
+__attribute__((visibility("default"))) void emu_band_publish(void *h, uint32_t *rec)
+{
+  EmuBand *b = static_cast<EmuBand *>(h);
+  const b2c::B2cSeamBand s = emu_seam_band(b);
+  const int run = ++b->run;
+  emu::launch(dim3(1), dim3(EMU_SEAM_THREADS), b2c::seam_smem_bytes(b->P.wpr), false, [=] { b2c::k_seam_publish(s, rec, run); });
+}
+__attribute__((visibility("default"))) int emu_band_solve(void *h, const uint32_t *all_records, int world, int rank)
+{
+  EmuBand *b = static_cast<EmuBand *>(h);
+  const b2c::B2cSeamBand s = emu_seam_band(b);
+  b2c::B2cSeamAll a;
+  memset(&a, 0, sizeof(a));
+  const size_t stride = b2c::seam_rec_words(b->P.wpr);
+  for (int r = 0; r < world; ++r) a.rec[r] = all_records + r * stride;
+  a.world = world; a.rank = rank; a.P = b->sP.data(); a.pre = b->pre.data();
+  emu::launch(dim3(1), dim3(EMU_SEAM_THREADS), b2c::seam_smem_bytes(b->P.wpr), false, [=] { b2c::k_seam_solve(s, a); });
+  B2cHystParams p = b->P.params(b->edges.data());
+  p.need = b->ctl;
+  int *bcp = b->P.bc.data();
+  const int tx = 32, ty = 4;
+  const dim3 gr((b->P.wpr + tx - 1) / tx, (b->P.h + 2 * ty - 1) / (2 * ty), 1), br(tx, ty);
+  emu::launch(gr, br, 0, false, [=] { b2c::k_uf_resolve<true, true>(p, bcp); });
+  return b->ctl[3];
+}
+__attribute__((visibility("default"))) void emu_band_edges(void *h, uint8_t *out)
+{
+  EmuBand *b = static_cast<EmuBand *>(h);
+  memcpy(out, b->edges.data(), b->edges.size());
 }
 }

@@ -35,7 +35,21 @@ def lib():
         _lib.emu_set_channels.restype = None
         _lib.emu_set_channels.argtypes = [_i]
         _lib.emu_hysteresis.restype = _i
-        _lib.emu_hysteresis.argtypes = [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, C.POINTER(_i)]
+        _lib.emu_hysteresis.argtypes = [_vp, _i, _i, _i, _vp, _vp]
+        _lib.emu_band_create.restype = _vp
+        _lib.emu_band_create.argtypes = [_i, _i]
+        _lib.emu_band_destroy.restype = None
+        _lib.emu_band_destroy.argtypes = [_vp]
+        _lib.emu_seam_words.restype = _i
+        _lib.emu_seam_words.argtypes = [_i]
+        _lib.emu_band_hysteresis.restype = None
+        _lib.emu_band_hysteresis.argtypes = [_vp, _vp]
+        _lib.emu_band_publish.restype = None
+        _lib.emu_band_publish.argtypes = [_vp, _vp]
+        _lib.emu_band_solve.restype = _i
+        _lib.emu_band_solve.argtypes = [_vp, _vp, _i, _i]
+        _lib.emu_band_edges.restype = None
+        _lib.emu_band_edges.argtypes = [_vp, _vp]
     return _lib
 
 
@@ -65,18 +79,49 @@ def stencil(bgr, lo=10, hi=40, impl=1, stages=False, y0=0, h_glob=None, rows=Non
     return out
 
 
-def hysteresis(map2, w, grid_blocks=3, tile_rows=4, ghost_top=None, ghost_bot=None):
+class Band:
+    """One row band with retained planes and union-find forest (the emulated twin of a b2c band handle)."""
+
+    def __init__(self, w, h):
+        self.w, self.h = w, h
+        self._h = lib().emu_band_create(w, h)
+        self.seam_words = lib().emu_seam_words(w)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().emu_band_destroy(self._h)
+            self._h = None
+
+    def hysteresis(self, map2):
+        m = np.ascontiguousarray(map2, np.uint32)
+        lib().emu_band_hysteresis(self._h, m.ctypes.data)
+
+    def publish(self):
+        rec = np.zeros(self.seam_words, np.uint32)
+        lib().emu_band_publish(self._h, rec.ctypes.data)
+        return rec
+
+    def solve(self, all_records, world, rank):
+        a = np.ascontiguousarray(all_records, np.uint32)
+        return lib().emu_band_solve(self._h, a.ctypes.data, world, rank)
+
+    def edges(self):
+        out = np.zeros((self.h, self.w), np.uint8)
+        lib().emu_band_edges(self._h, out.ctypes.data)
+        return out
+
+
+def hysteresis(map2, w, want_edges=True):
+    """(n, h, gpr) or (h, gpr) 2-bit maps -> (u8 edge maps or None, edge bit planes)."""
     m = np.ascontiguousarray(map2, np.uint32)
     if m.ndim == 2:
         m = m[None]
     n, h, _ = m.shape
-    edges = np.zeros((n, h, w), np.uint8)
+    edges = np.zeros((n, h, w), np.uint8) if want_edges else None
     bits = np.zeros((n, h, (w + 31) // 32), np.uint32)
-    ch = C.c_int(0)
-    gt = None if ghost_top is None else np.ascontiguousarray(ghost_top, np.uint32).ctypes.data
-    gb = None if ghost_bot is None else np.ascontiguousarray(ghost_bot, np.uint32).ctypes.data
-    rounds = lib().emu_hysteresis(m.ctypes.data, w, h, n, grid_blocks, tile_rows, edges.ctypes.data, bits.ctypes.data, gt, gb, C.byref(ch))
-    return edges, bits, rounds, ch.value
+    rc = lib().emu_hysteresis(m.ctypes.data, w, h, n, None if edges is None else edges.ctypes.data, bits.ctypes.data)
+    assert rc == 0
+    return edges, bits
 
 
 def stencil_raw(buf, row0, w, h, lo=10, hi=40, impl=0, y0=0, h_glob=None, channels=3):

@@ -47,28 +47,28 @@ def test_march_stencil_map(kind, w, h, seed, lo, hi, rb):
     assert e is not None and np.array_equal(e, O.thresh_to_map2(r["thresh"]))
 
 
-@pytest.mark.parametrize("tile_rows", [-1, 0, 4], ids=["unionfind4", "unionfind_coop", "tilerounds"])
 @pytest.mark.parametrize("kind,w,h,seed", [("scene", 200, 150, 7), ("noise", 97, 61, 8), ("steps", 130, 70, 9), ("scene", 1100, 40, 5)])
-def test_hysteresis_kernel(kind, w, h, seed, tile_rows):
+def test_hysteresis_kernel(kind, w, h, seed):
     f = synth.frame(kind, seed, w, h)
     r = O.canny(f)
-    edges, bits, rounds, changed = E.hysteresis(O.thresh_to_map2(r["thresh"]), w, grid_blocks=3, tile_rows=tile_rows)
+    edges, bits = E.hysteresis(O.thresh_to_map2(r["thresh"]), w)
     assert np.array_equal(edges[0], r["edges"])
     assert np.array_equal(bits[0], O.edges_to_bits(r["edges"]))
+    # bit plane only (the u8 map is optional in the product: b2c_run_batch_* with edges == null)
+    none, bits2 = E.hysteresis(O.thresh_to_map2(r["thresh"]), w, want_edges=False)
+    assert none is None and np.array_equal(bits2, bits)
 
 
-@pytest.mark.parametrize("tile_rows", [-1, 0], ids=["unionfind4", "unionfind_coop"])
 @pytest.mark.parametrize("dens", [0.1, 0.3, 0.5])
-def test_hysteresis_unionfind_random_maps(dens, tile_rows):
+def test_hysteresis_unionfind_random_maps(dens):
     rng = np.random.default_rng(int(dens * 10))
     t = np.where(rng.random((90, 131)) < dens, 128, 0).astype(np.uint8)
     t[rng.random(t.shape) < 0.002] = 255
-    edges, _, _, _ = E.hysteresis(O.thresh_to_map2(t), 131, grid_blocks=4, tile_rows=tile_rows)
+    edges, _ = E.hysteresis(O.thresh_to_map2(t), 131)
     assert np.array_equal(edges[0], O.hysteresis(t))
 
 
-@pytest.mark.parametrize("tile_rows", [-1, 0, 4], ids=["unionfind4", "unionfind_coop", "tilerounds"])
-def test_hysteresis_long_chain_and_batch(tile_rows):
+def test_hysteresis_long_chain_and_batch():
     # a weak spiral seeded by a single strong pixel: worst case for tile-local propagation
     w, h = 70, 40
     t = np.zeros((h, w), np.uint8)
@@ -80,7 +80,7 @@ def test_hysteresis_long_chain_and_batch(tile_rows):
     t[2, 2] = 255
     t[20, 30] = 128   # isolated weak pixel: must vanish
     m = np.stack([O.thresh_to_map2(t), O.thresh_to_map2(np.zeros_like(t))])
-    edges, bits, rounds, changed = E.hysteresis(m, w, grid_blocks=2, tile_rows=tile_rows)
+    edges, bits = E.hysteresis(m, w)
     assert np.array_equal(edges[0], O.hysteresis(t)) and edges[0][20, 30] == 0 and edges[0][6, w - 7] == 255
     assert not edges[1].any()
 
@@ -119,26 +119,13 @@ def test_march_band_mode_equals_whole_image(impl):
         assert np.array_equal(band, whole[y0:y0 + rows]), (y0, rows)
 
 
-def test_hysteresis_unionfind_word_list_overflow():
-    """More words with weak pixels per warp than the per-warp list holds: the kernel falls back to the plain scan."""
+def test_hysteresis_wide_dense_map():
+    """8 tile columns of dense clutter: long border lists between the 32-row x 256-pixel tiles."""
     rng = np.random.default_rng(5)
     t = np.where(rng.random((80, 2048)) < 0.2, 128, 0).astype(np.uint8)
     t[rng.random(t.shape) < 0.001] = 255
-    edges, _, _, _ = E.hysteresis(O.thresh_to_map2(t), 2048, grid_blocks=1, tile_rows=0)
+    edges, _ = E.hysteresis(O.thresh_to_map2(t), 2048)
     assert np.array_equal(edges[0], O.hysteresis(t))
-
-
-def test_hysteresis_unionfind4_ghost_rows_and_reentry():
-    """Row-band mode: strong bits in the ghost rows seed the band; the second pass re-enters on the retained planes."""
-    w, h = 100, 20
-    t = np.zeros((h, w), np.uint8)
-    t[0:h, 10] = 128          # reaches the top ghost row
-    t[5:h, 50] = 128          # reaches the bottom ghost row only
-    t[3:10, 80] = 128         # touches nothing
-    gt = np.zeros((w + 31) // 32, np.uint32); gt[0] = 1 << 11   # strong pixel at (-1, 11): diagonal neighbour of (0, 10)
-    gb = np.zeros((w + 31) // 32, np.uint32); gb[1] = 1 << (50 - 32)
-    edges, bits, _, changed = E.hysteresis(O.thresh_to_map2(t), w, grid_blocks=2, tile_rows=-1, ghost_top=gt, ghost_bot=gb)
-    assert edges[0][:, 10].all() and edges[0][5:, 50].all() and not edges[0][:, 80].any() and not edges[0][:5, 50].any()
 
 
 @pytest.mark.parametrize("dens,seed", [(0.08, 1), (0.25, 2), (0.6, 3)])
@@ -152,7 +139,7 @@ def test_hysteresis_unionfind4_many_tiles(dens, seed):
     # long chains along and across the tile borders
     t[31:33, 100:500] = np.where(t[31:33, 100:500] == 255, 255, 128)
     t[5:70, 255:257] = np.where(t[5:70, 255:257] == 255, 255, 128)
-    edges, bits, _, _ = E.hysteresis(O.thresh_to_map2(t), w, grid_blocks=2, tile_rows=-1)
+    edges, bits = E.hysteresis(O.thresh_to_map2(t), w)
     want = O.hysteresis(t)
     assert np.array_equal(edges[0], want)
     assert np.array_equal(bits[0], O.edges_to_bits(want))
@@ -167,7 +154,7 @@ def test_hysteresis_unionfind4_diagonal_staircase_across_tiles():
         t[5 + i, 290 - i] = 128          # down-left through (32 + ..., 256)
     t[5, 225] = 255
     t[64, 231] = 255
-    edges, _, _, _ = E.hysteresis(O.thresh_to_map2(t), w, grid_blocks=2, tile_rows=-1)
+    edges, _ = E.hysteresis(O.thresh_to_map2(t), w)
     assert np.array_equal(edges[0], O.hysteresis(t))
 
 

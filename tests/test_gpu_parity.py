@@ -82,23 +82,43 @@ def test_live_reference_kernels_720p():
     ref.close()
 
 
-@pytest.mark.parametrize("hyst_impl", [0, 1, 2], ids=["unionfind4", "tilerounds", "unionfind_coop"])
-def test_hysteresis_impls_and_worst_cases(hyst_impl):
-    """Both on-device hysteresis schemes against the fixpoint oracle, incl. a 1910-px weak line seeded at one end
-    (65 reference launches) and a dense random map."""
+def test_hysteresis_worst_cases_and_launch_count():
+    """On-device hysteresis against the fixpoint oracle, incl. a 1910-px weak line seeded at one end (65
+    reference launches) and a dense random map; the launch count is fixed: 1 stencil + 3 hysteresis, whatever the chain
+    length (the reference relaunches until a flag stays clear, capped at 100: cannyEdgeH.cu:297-338)."""
+    from cudacam_b200 import _lib
     w, h = 1920, 64
     f = synth.frame("scene", 77, w, h)
     with cb.CannyEdge(w, h) as c:
-        c.set_option("hyst_impl", hyst_impl)
         c.run(f)
+        n0 = _lib.lib.b2c_launch_count(c._h)
+        c.run(f)
+        assert _lib.lib.b2c_launch_count(c._h) - n0 == 4
         assert np.array_equal(c.edges(), O.canny(f)["edges"])
     for kind, ww, hh, seed in (("noise", 640, 360, 5), ("steps", 800, 600, 6), ("scene", 3840, 2160, 9)):
         f = synth.frame(kind, seed, ww, hh)
         with cb.CannyEdge(ww, hh) as c:
-            c.set_option("hyst_impl", hyst_impl)
             c.run(f)
             th = c.thresh()
             assert np.array_equal(c.edges(), O.hysteresis(th)), (kind, ww, hh)
+
+
+def test_buffer_state_rules():
+    """EDGES / BITS exist only after a run that reached HYSTER (no stale maps from an earlier frame); stage buffers of a
+    device-resident run are rebuilt from the caller's input only while the handle still knows it."""
+    w, h = 320, 200
+    f, g = synth.frame("scene", 1, w, h), synth.frame("scene", 2, w, h)
+    with cb.CannyEdge(w, h) as c:
+        c.run(f)
+        assert np.array_equal(c.edges(), O.canny(f)["edges"])
+        c.run(g, cb.CannyStage.THRESH)
+        assert np.array_equal(c.thresh(), O.canny(g)["thresh"])
+        with pytest.raises(cb.B2cError):
+            c.edges()
+        with pytest.raises(cb.B2cError):
+            c.bits()
+        c.run(g)
+        assert np.array_equal(c.edges(), O.canny(g)["edges"])
 
 
 def test_strided_input_and_threshold_api():
