@@ -50,15 +50,15 @@ _SIGS = {
     "b2c_band_stencil": (_i, [_vp, _u8p, _sz, _vp]),
     "b2c_band_hysteresis": (_i, [_vp, _vp]),
     "b2c_band_seam_bytes": (_i, [_vp, C.POINTER(_sz)]),
-    "b2c_band_seam_publish": (_i, [_vp, C.POINTER(_vp), _vp]),
+    "b2c_band_seam_record": (_i, [_vp, C.POINTER(_vp)]),
     "b2c_band_seam_solve": (_i, [_vp, _vp, _i, _i, _vp]),
     "b2c_band_status": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
     "b2c_band_input": (_i, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
     "b2c_band_p2p_export": (_i, [_vp, _vp]),
     "b2c_band_p2p_open": (_i, [_vp, _vp, _i, _i]),
     "b2c_band_p2p_open_local": (_i, [_vp, C.POINTER(_vp), _i, _i]),
-    "b2c_band_p2p_halo": (_i, [_vp, _vp, _i]),
-    "b2c_band_p2p_seam": (_i, [_vp, _vp, _i]),
+    "b2c_band_p2p_stencil": (_i, [_vp, _vp, _i]),
+    "b2c_band_p2p_seam": (_i, [_vp, _vp]),
     "b2c_strerror": (C.c_char_p, [_i]),
     "b2c_last_cuda_error": (C.c_char_p, [_vp]),
     "b2c_version": (C.c_char_p, []),

@@ -2,11 +2,11 @@
 
 No reference counterpart: the reference is single-GPU.  Each rank owns a contiguous band of rows.
 The fused stencil needs 4 rows of INPUT beyond each interior seam (2 Gaussian + 1 Sobel + 1 NMS), exchanged once with
-the neighbours; the reference's zero padding applies only at the true image border.  Hysteresis: every rank resolves
-its band on the device (union-find kernels) and keeps planes and forest; then ONE exchange: every rank publishes its
-seam record (edge / unresolved-weak bit rows of its first and last row + a component label per unresolved run), the
-records are all-gathered, and every rank solves the same small connected-components problem over all seams and
-promotes its own components that reach an edge pixel of any band.  The result is bit-identical to the unsharded run
+the neighbours; the reference's zero padding applies only at the true image border.  Hysteresis: every rank builds the
+union-find forest of its band, writes its seam record (edge / unresolved-weak bit rows of its first and last row + a
+component label per unresolved run) and resolves the band while the record travels; then ONE exchange: the records
+are all-gathered, and every rank solves the same small connected-components problem over all seams and promotes its own
+components that reach an edge pixel of any band.  The result is bit-identical to the unsharded run
 because both compute the same fixpoint.
 
 Transports: peer memory (ranks of one box: halo rows and records are plain stores into the peers' mapped buffers) or
@@ -95,14 +95,15 @@ class CudaBandBackend:
         _lib.check(_lib.lib.b2c_band_stencil(self._h, ptr, self.row_stride, self._stream()), self._h, "b2c_band_stencil")
 
     def hysteresis(self):
-        """Band-local fixpoint (planes and forest are kept for the seam solve); writes the u8 edge map."""
+        """Band-local fixpoint (planes and forest are kept for the seam solve); writes the u8 edge map and the band's
+        seam record (with peer wiring: also into every rank's mailbox)."""
         _lib.check(_lib.lib.b2c_band_hysteresis(self._h, self._stream()), self._h, "b2c_band_hysteresis")
 
     # -- cross-band hysteresis: collective transport -------------------------------------------------------------
     def seam_record(self):
-        """Publishes this band's seam record; returns it as a uint8 device tensor (owned by the handle)."""
+        """This band's seam record as a uint8 device tensor (owned by the handle, written by hysteresis())."""
         p = C.c_void_p()
-        _lib.check(_lib.lib.b2c_band_seam_publish(self._h, C.byref(p), self._stream()), self._h, "b2c_band_seam_publish")
+        _lib.check(_lib.lib.b2c_band_seam_record(self._h, C.byref(p)), self._h, "b2c_band_seam_record")
         return self.torch.as_tensor(_DevArray(p.value, self.seam_bytes, "|u1"), device=f"cuda:{self.device}")
 
     def gather_buffer(self, world):
@@ -125,12 +126,24 @@ class CudaBandBackend:
         _lib.check(_lib.lib.b2c_band_p2p_open(self._h, buf, world, rank), self._h, "b2c_band_p2p_open")
         self.p2p = True
 
-    def halo_p2p(self, phase=0):
-        """phase: 0 = push + wait (one band per process), 1 = push, 2 = wait (see run_local)."""
-        _lib.check(_lib.lib.b2c_band_p2p_halo(self._h, self._stream(), phase), self._h, "b2c_band_p2p_halo")
+    def stencil_p2p(self, phase=0):
+        """Halo exchange over peer memory hidden behind the stencil of the rows that need no halo.
+        phase: 0 = all (one band per process), 1 = push + interior rows, 2 = wait + seam strips (see run_local)."""
+        _lib.check(_lib.lib.b2c_band_p2p_stencil(self._h, self._stream(), phase), self._h, "b2c_band_p2p_stencil")
 
-    def seam_p2p(self, phase=0):
-        _lib.check(_lib.lib.b2c_band_p2p_seam(self._h, self._stream(), phase), self._h, "b2c_band_p2p_seam")
+    def seam_p2p(self):
+        _lib.check(_lib.lib.b2c_band_p2p_seam(self._h, self._stream()), self._h, "b2c_band_p2p_seam")
+
+    def seam_phase_us(self):
+        """Phase times of the last hysteresis + seam pass (needs set_phase_timing(True)): dict of microseconds."""
+        names = ("tile_border", "publish_push", "resolve", "gap", "wait_solve", "list_pass")
+        d = {n: _lib.lib.b2c_get_info(self._h, b"seam_phase_us%d" % k) for k, n in enumerate(names)}
+        if self.p2p:
+            d.update({n: _lib.lib.b2c_get_info(self._h, b"band_stencil_us%d" % k) for k, n in enumerate(("push_interior", "halo_wait", "strips"))})
+        return d
+
+    def set_phase_timing(self, on):
+        _lib.check(_lib.lib.b2c_set_option(self._h, b"hyst_phase_timing", 1 if on else 0), self._h, "b2c_set_option")
 
     def status(self):
         """(weak runs promoted by the last solve, peer time-out flag) -- blocking."""
@@ -140,6 +153,13 @@ class CudaBandBackend:
 
     def sync(self):
         self.torch.cuda.synchronize(self.device)
+
+    def mark(self):
+        """An event recorded on the stream the band's work is launched on (torch's current stream)."""
+        assert not self.own_stream
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record(self.torch.cuda.current_stream(self.device))
+        return e
 
     @property
     def launches(self):
@@ -184,31 +204,59 @@ class BandCanny:
             r.wait()
 
     def exchange_input_halos(self):
+        """Collective transport: the 4 input rows on either side of every seam by send / recv."""
         b, n = self.b, self.b.rows
         if self.world == 1:
             return
-        if getattr(b, "p2p", False):
-            b.halo_p2p()   # peer stores into the neighbours' buffers + device-side arrival counters
-            return
         self._exchange(b.input_rows(HALO, 2 * HALO), b.input_rows(0, HALO), b.input_rows(n, n + HALO), b.input_rows(n + HALO, n + 2 * HALO))
+
+    def stencil(self):
+        """Halo exchange + stencil of the band (peer memory: the exchange is hidden behind the interior rows)."""
+        b = self.b
+        if self.world > 1 and getattr(b, "p2p", False):
+            b.stencil_p2p()
+        else:
+            self.exchange_input_halos()
+            b.stencil()
+
+    def seam_exchange(self):
+        """Cross-band hysteresis: all-gather of the records, solve.  Returns the number of exchanges (0 or 1)."""
+        b = self.b
+        if self.world == 1:
+            return 0
+        if getattr(b, "p2p", False):
+            b.seam_p2p()
+        else:
+            rec = b.seam_record()
+            allr = b.gather_buffer(self.world)
+            self.dist.all_gather_into_tensor(allr, rec, group=self.group)
+            b.seam_solve(allr, self.world, self.rank)
+        return 1
 
     def run(self):
         """Stencil + hysteresis of this band; returns the number of cross-band exchanges (0 or 1)."""
-        b = self.b
-        self.exchange_input_halos()
-        b.stencil()
-        b.hysteresis()
-        self.exchanges = 0
-        if self.world > 1:
-            if getattr(b, "p2p", False):
-                b.seam_p2p()
-            else:
-                rec = b.seam_record()
-                allr = b.gather_buffer(self.world)
-                self.dist.all_gather_into_tensor(allr, rec, group=self.group)
-                b.seam_solve(allr, self.world, self.rank)
-            self.exchanges = 1
+        self.stencil()
+        self.b.hysteresis()
+        self.exchanges = self.seam_exchange()
         return self.exchanges
+
+    def phase_times(self, reps=5):
+        """`reps` more runs with an event after every phase: median microseconds of halo exchange + stencil, band-local
+        hysteresis and seam pass on this rank (waits for the peers included).  None if the backend has no events."""
+        b = self.b
+        if not hasattr(b, "mark"):
+            return None
+        names = ("stencil_us", "hysteresis_us", "seam_us")
+        acc = {k: [] for k in names}
+        for _ in range(reps):
+            m = [b.mark()]
+            for step in (self.stencil, b.hysteresis, self.seam_exchange):
+                step()
+                m.append(b.mark())
+            b.sync()
+            for i, k in enumerate(names):
+                acc[k].append(1e3 * m[i].elapsed_time(m[i + 1]))
+        return {k: sorted(v)[len(v) // 2] for k, v in acc.items()}
 
 
 def run_local(backends, stencil=True):
@@ -223,9 +271,9 @@ def run_local(backends, stencil=True):
     if stencil:
         if p2p:   # every push is issued before the first wait
             for b in backends:
-                b.halo_p2p(1)
+                b.stencil_p2p(1)
             for b in backends:
-                b.halo_p2p(2)
+                b.stencil_p2p(2)
         else:
             for i in range(n - 1):
                 up, dn = backends[i], backends[i + 1]
@@ -233,16 +281,14 @@ def run_local(backends, stencil=True):
                 up.input_rows(up.rows + HALO, up.rows + 2 * HALO).copy_(dn.input_rows(HALO, 2 * HALO), non_blocking=True)
             for b in backends:
                 b.sync()
-        for b in backends:
-            b.stencil()
+            for b in backends:
+                b.stencil()
     for b in backends:
-        b.hysteresis()
+        b.hysteresis()   # (peer wiring: includes the push of the seam record)
     if n > 1:
         if p2p:
             for b in backends:
-                b.seam_p2p(1)
-            for b in backends:
-                b.seam_p2p(2)
+                b.seam_p2p()
         else:
             recs = [b.seam_record() for b in backends]
             for b in backends:

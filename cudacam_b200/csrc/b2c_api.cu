@@ -97,9 +97,14 @@ struct b2c_ctx {
   int band_y0 = 0, h_glob = 0;
   // band mode: seam records (k_band_seam.cuh); peer-to-peer: own mailbox, the other ranks' mailboxes mapped through CUDA IPC
   uint32_t *d_seam_rec = nullptr;          // own record (NCCL / gloo all-gather path)
-  int *d_seam_roots = nullptr, *d_seam_hkey = nullptr, *d_seam_hval = nullptr, *d_seam_P = nullptr, *d_seam_pre = nullptr;
-  int *d_seam_ctl = nullptr, *h_seam_ctl = nullptr;
+  int *d_seam_roots = nullptr, *d_seam_hkey = nullptr, *d_seam_hval = nullptr, *d_seam_P = nullptr;
+  int *d_seam_ctl = nullptr, *h_seam_ctl = nullptr;   // [0] promoted flag, [2] peer time-out, [3] runs promoted, [4] length of ulist
+  uint2 *d_ulist = nullptr;                // plane words that keep unresolved weak pixels after the band-local resolve
+  int ucap = 0;
+  cudaEvent_t ev_b[4] = {};                // phase marks of b2c_band_p2p_stencil: start, after push + interior rows, after the wait, end
+  cudaEvent_t ev_s[7] = {};                // phase marks of the band hysteresis / seam pass (hyst_phase_timing option)
   int seam_run = 0;
+  bool seam_force_global = false;          // test option: global-memory hash / forest in the seam kernels
   uint32_t *d_mailbox = nullptr;
   void *peer_mail[b2c::BP_MAXW] = {};
   void *peer_in[2] = { nullptr, nullptr };   // band input buffers of the upper / lower neighbour
@@ -372,6 +377,10 @@ int b2c_create(b2c_handle *out, int device, int width, int height, int channels,
   return B2C_OK;
 }
 
+namespace
+{
+int seam_alloc(b2c_ctx *c);
+}
 int b2c_create_band(b2c_handle *out, int device, int width, int band_rows, int y0, int height_global)
 {
   if (!out || width < 1 || band_rows < 1 || y0 < 0 || y0 + band_rows > height_global) return B2C_ERR_INVALID;
@@ -395,6 +404,7 @@ int b2c_create_band(b2c_handle *out, int device, int width, int band_rows, int y
   c->h_glob = height_global;
   DevGuard g(device);
   int rc = alloc_common(c);
+  if (rc == B2C_OK) rc = seam_alloc(c);
   if (rc != B2C_OK) {
     fprintf(stderr, "[b200canny] b2c_create_band failed: %s\n", c->last_err.c_str());
     b2c_destroy(c);
@@ -438,8 +448,12 @@ void b2c_destroy(b2c_handle c)
   cudaFree(c->d_seam_hkey);
   cudaFree(c->d_seam_hval);
   cudaFree(c->d_seam_P);
-  cudaFree(c->d_seam_pre);
   cudaFree(c->d_seam_ctl);
+  cudaFree(c->d_ulist);
+  for (auto &e : c->ev_s)
+    if (e) cudaEventDestroy(e);
+  for (auto &e : c->ev_b)
+    if (e) cudaEventDestroy(e);
   if (c->h_seam_ctl) cudaFreeHost(c->h_seam_ctl);
   cudaFree(c->d_blist);
   cudaFree(c->d_bcount);
@@ -871,26 +885,13 @@ int b2c_load_thresh(b2c_handle c, const uint8_t *host_thresh, size_t row_stride)
 }
 
 // ---- row-band mode --------------------------------------------------------------------------------
-int b2c_band_stencil(b2c_handle c, const uint8_t *dev_bgr_band_row0, size_t row_stride, void *stream)
-{
-  if (!c || !c->band || !dev_bgr_band_row0) return B2C_ERR_INVALID;
-  if (row_stride < (size_t)c->w * 3) return B2C_ERR_SIZE;
-  DevGuard g(c->dev);
-  cudaStream_t st = stream ? (cudaStream_t)stream : c->s_main;
-  c->have_frame = true;
-  return launch_stencil(c, dev_bgr_band_row0, row_stride, 0, 1, st);
-}
-
-int b2c_band_hysteresis(b2c_handle c, void *stream)
-{
-  if (!c || !c->band) return B2C_ERR_INVALID;
-  DevGuard g(c->dev);
-  return launch_hysteresis(c, 1, c->d_edges, c->edges_pitch, c->edges_frame_stride, stream ? (cudaStream_t)stream : c->s_main);
-}
-
+// Order of one band step (stream order; [p2p] = only with peer wiring):
+//   [halo push] stencil interior rows [halo wait] stencil edge rows | k_uf_tile, k_uf_border, k_seam_publish [+ push],
+//   k_uf_resolve<LIST> | k_seam_solve [waits for the peers' records first], k_uf_resolve_list
+// The halo rows travel while the interior rows are computed, the seam records while the band resolves.
 namespace
 {
-// scratch of the seam kernels, allocated on first use
+// scratch of the seam kernels
 int seam_alloc(b2c_ctx *c)
 {
   if (c->d_seam_rec) return B2C_OK;
@@ -900,22 +901,23 @@ int seam_alloc(b2c_ctx *c)
   CK(c, cudaMalloc(&c->d_seam_roots, (size_t)2 * cap * sizeof(int)));
   CK(c, cudaMalloc(&c->d_seam_hkey, (size_t)hs * sizeof(int)));
   CK(c, cudaMalloc(&c->d_seam_hval, (size_t)hs * sizeof(int)));
+  CK(c, cudaMemset(c->d_seam_hkey, 0, (size_t)hs * sizeof(int)));
   CK(c, cudaMalloc(&c->d_seam_P, ((size_t)b2c::SEAM_MAXW * 2 * cap + 1) * sizeof(int)));
-  CK(c, cudaMalloc(&c->d_seam_pre, (size_t)b2c::SEAM_MAXW * 2 * c->wpr * sizeof(int)));
   CK(c, cudaMalloc(&c->d_seam_ctl, 8 * sizeof(int)));
   CK(c, cudaMemset(c->d_seam_ctl, 0, 8 * sizeof(int)));
   CK(c, cudaMallocHost(&c->h_seam_ctl, 8 * sizeof(int)));
   memset(c->h_seam_ctl, 0, 8 * sizeof(int));
-  const size_t dyn = b2c::seam_smem_bytes(c->wpr);
-  if (dyn > 48 * 1024) {
-    CK(c, cudaFuncSetAttribute(b2c::k_seam_publish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    CK(c, cudaFuncSetAttribute(b2c::k_seam_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-  }
+  c->ucap = (int)std::max<long long>(4096, (long long)c->wpr * c->rows_alloc / 4);
+  CK(c, cudaMalloc(&c->d_ulist, (size_t)c->ucap * sizeof(uint2)));
+  CK(c, cudaFuncSetAttribute(b2c::k_seam_publish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b2c::seam_publish_smem(4095)));
+  CK(c, cudaFuncSetAttribute(b2c::k_seam_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b2c::seam_solve_smem()));
+  for (auto &e : c->ev_s) CK(c, cudaEventCreate(&e));
+  for (auto &e : c->ev_b) CK(c, cudaEventCreate(&e));
   return B2C_OK;
 }
 void fill_seam_band(b2c_ctx *c, b2c::B2cSeamBand &b)
 {
-  b.S = E0(c);   // "edges so far" of the band: strong | locally promoted
+  b.S = S0(c);
   b.C = C0(c);
   b.plane_pitch = c->plane_pitch;
   b.wpr = c->wpr;
@@ -925,21 +927,98 @@ void fill_seam_band(b2c_ctx *c, b2c::B2cSeamBand &b)
   b.hkey = c->d_seam_hkey;
   b.hval = c->d_seam_hval;
   b.hsize = b2c::seam_hash_size(c->wpr);
+  b.shash = c->seam_force_global ? 0 : b2c::SEAM_SHASH;
+  b.snodes = c->seam_force_global ? 0 : b2c::SEAM_SNODES;
   b.ctl = c->d_seam_ctl;
 }
-int seam_publish(b2c_ctx *c, uint32_t *rec, cudaStream_t st)
+uint32_t *own_mail(b2c_ctx *c) { return (uint32_t *)c->peer_mail[c->p2p_rank]; }
+
+// rows [r0, r0 + nrows) of the band through the fused stencil
+int launch_stencil_rows(b2c_ctx *c, const uint8_t *band_row0, size_t row_stride, int r0, int nrows, cudaStream_t st)
 {
+  if (nrows <= 0) return B2C_OK;
+  B2cStencilParams p;
+  fill_stencil_params(c, p, band_row0 + (size_t)r0 * row_stride, row_stride, 0, 1);
+  p.h = nrows;
+  p.y0 = c->band_y0 + r0;
+  p.pl_S += (long long)r0 * p.pl_pitch16;
+  p.pl_C += (long long)r0 * p.pl_pitch16;
+  // (a strip of a few rows: 256-thread tiles finish sooner than one-warp CTAs marching 12 rows each)
+  if (c->stencil_impl == 0 && nrows > 8 && b2c::march_supported(p)) {
+    cudaError_t e = b2c::march_launch(p, c->sm_count, c->march_ctas_per_sm, r0 == 0 && nrows == c->rows_alloc ? c->march_rb : 0, st, c->march_extra_smem);
+    if (e != cudaSuccess) return set_err(c, e, "k_stencil_march launch");
+  } else {
+    dim3 grid((c->w + b2c::TILE_W - 1) / b2c::TILE_W, (nrows + b2c::TILE_H - 1) / b2c::TILE_H, 1);
+    b2c::k_stencil_tile<false><<<grid, b2c::TILE_THREADS, b2c::TILE_SMEM, st>>>(p);
+    CK(c, cudaGetLastError());
+  }
+  c->launches++;
+  c->map2_valid = false;
+  c->edges_valid = false;
+  c->have_frame = true;
+  return B2C_OK;
+}
+}// namespace
+
+int b2c_band_stencil(b2c_handle c, const uint8_t *dev_bgr_band_row0, size_t row_stride, void *stream)
+{
+  if (!c || !c->band || !dev_bgr_band_row0) return B2C_ERR_INVALID;
+  if (row_stride < (size_t)c->w * 3) return B2C_ERR_SIZE;
+  DevGuard g(c->dev);
+  return launch_stencil_rows(c, dev_bgr_band_row0, row_stride, 0, c->rows_alloc, stream ? (cudaStream_t)stream : c->s_main);
+}
+
+// Band-local hysteresis.  The seam record is built as soon as the forest is complete (and, with peer wiring, pushed to
+// every rank) so that it travels while the band resolves.
+int b2c_band_hysteresis(b2c_handle c, void *stream)
+{
+  if (!c || !c->band) return B2C_ERR_INVALID;
+  DevGuard g(c->dev);
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->s_main;
+  B2cHystParams p;
+  fill_hyst_params(c, p, 1, c->d_edges, c->edges_pitch, c->edges_frame_stride);
+  const bool pt = c->hyst_phase_timing;
+  if (pt) cudaEventRecord(c->ev_s[0], st);
+  const dim3 gt((c->wpr + b2c::UT_WORDS - 1) / b2c::UT_WORDS, (c->rows_alloc + b2c::UT_ROWS - 1) / b2c::UT_ROWS, 1);
+  const int T = b2c::UFK_THREADS;
+  b2c::k_uf_tile<<<gt, b2c::UT_THREADS, b2c::UT_SMEM, st>>>(p, c->d_blist, c->d_bcount, c->bcap);
+  b2c::k_uf_border<<<dim3(std::max(1, (c->bcap + T - 1) / T), 1, 1), T, 0, st>>>(p, c->d_blist, c->d_bcount, c->bcap);
+  if (pt) cudaEventRecord(c->ev_s[1], st);
+  // seam record
   b2c::B2cSeamBand b;
   fill_seam_band(c, b);
   c->seam_run += 1;
-  const size_t dyn = b2c::seam_smem_bytes(c->wpr);
-  b2c::k_seam_publish<<<1, b2c::SEAM_THREADS, dyn, st>>>(b, rec, c->seam_run);
+  const int world = c->p2p_world, rank = c->p2p_rank, par = c->seam_run & 1;
+  const bool p2p = world >= 2 && c->d_mailbox;
+  uint32_t *rec = p2p ? own_mail(c) + b2c::bp_seam_slot(c->wpr, par, rank) : c->d_seam_rec;
+  b2c::B2cSeamPeers q;
+  memset(&q, 0, sizeof(q));
+  if (p2p) {   // the publishing CTA also stores the record into every rank's mailbox
+    for (int k = 0; k < world; ++k) {
+      q.slot[k] = (uint32_t *)c->peer_mail[k] + b2c::bp_seam_slot(c->wpr, par, rank);
+      q.flag[k] = (uint32_t *)c->peer_mail[k] + b2c::bp_seam_flag(c->wpr, par, rank);
+    }
+    q.world = world;
+    q.rank = rank;
+  }
+  b2c::k_seam_publish<<<1, b2c::SEAM_THREADS, b2c::seam_publish_smem(c->wpr), st>>>(b, rec, c->seam_run, q);
+  c->launches += 3;
+  if (pt) cudaEventRecord(c->ev_s[2], st);
+  // resolve + expansion; the words that stay unresolved go to the list of the seam pass
+  const int tx = c->wpr >= 256 ? 256 : c->wpr > 32 ? 64 : 32, ty = 256 / tx;
+  const dim3 gr((c->wpr + tx - 1) / tx, (c->rows_alloc + 2 * ty - 1) / (2 * ty), 1), br(tx, ty);
+  b2c::k_uf_resolve<true, true><<<gr, br, 0, st>>>(p, c->d_bcount, c->d_ulist, c->d_seam_ctl + 4, c->ucap);
+  if (pt) cudaEventRecord(c->ev_s[3], st);
   CK(c, cudaGetLastError());
   c->launches++;
+  c->edges_valid = true;
   return B2C_OK;
 }
-// solve on the gathered records + one resolve pass that promotes the components the solve hung under node 0
-int seam_solve(b2c_ctx *c, const uint32_t *const *recs, int world, int rank, cudaStream_t st)
+
+namespace
+{
+// solve on the gathered records + the pass over the still unresolved words that promotes what the solve hung under node 0
+int seam_solve(b2c_ctx *c, const uint32_t *const *recs, int world, int rank, const uint32_t *flags, cudaStream_t st)
 {
   b2c::B2cSeamBand b;
   fill_seam_band(c, b);
@@ -949,15 +1028,14 @@ int seam_solve(b2c_ctx *c, const uint32_t *const *recs, int world, int rank, cud
   a.world = world;
   a.rank = rank;
   a.P = c->d_seam_P;
-  a.pre = c->d_seam_pre;
-  const size_t dyn = b2c::seam_smem_bytes(c->wpr);
-  b2c::k_seam_solve<<<1, b2c::SEAM_THREADS, dyn, st>>>(b, a);
+  a.flags = flags;
+  a.run_id = c->seam_run;
+  b2c::k_seam_solve<<<1, b2c::SEAM_THREADS, b2c::seam_solve_smem(), st>>>(b, a);
+  if (c->hyst_phase_timing) cudaEventRecord(c->ev_s[5], st);
   B2cHystParams p;
   fill_hyst_params(c, p, 1, c->d_edges, c->edges_pitch, c->edges_frame_stride);
-  p.need = c->d_seam_ctl;   // ctl[0]: a root of this band was promoted
-  const int tx = c->wpr >= 256 ? 256 : c->wpr > 32 ? 64 : 32, ty = 256 / tx;
-  const dim3 gr((c->wpr + tx - 1) / tx, (c->rows_alloc + 2 * ty - 1) / (2 * ty), 1), br(tx, ty);
-  b2c::k_uf_resolve<true, true><<<gr, br, 0, st>>>(p, c->d_bcount);
+  b2c::k_uf_resolve_list<true><<<c->sm_count * 2, b2c::UFK_THREADS, 0, st>>>(p, c->d_ulist, c->d_seam_ctl + 4, c->ucap, c->d_seam_ctl);
+  if (c->hyst_phase_timing) cudaEventRecord(c->ev_s[6], st);
   CK(c, cudaGetLastError());
   c->launches += 2;
   return B2C_OK;
@@ -971,39 +1049,31 @@ int b2c_band_seam_bytes(b2c_handle c, size_t *bytes)
   return B2C_OK;
 }
 
-int b2c_band_seam_publish(b2c_handle c, void **record_dev, void *stream)
+int b2c_band_seam_record(b2c_handle c, void **record_dev)
 {
   if (!c || !c->band || !record_dev) return B2C_ERR_INVALID;
-  DevGuard g(c->dev);
-  int rc = seam_alloc(c);
-  if (rc != B2C_OK) return rc;
   *record_dev = c->d_seam_rec;
-  return seam_publish(c, c->d_seam_rec, stream ? (cudaStream_t)stream : c->s_main);
+  return B2C_OK;
 }
 
 int b2c_band_seam_solve(b2c_handle c, const void *all_records_dev, int world, int rank, void *stream)
 {
   if (!c || !c->band || !all_records_dev || world < 1 || world > b2c::SEAM_MAXW || rank < 0 || rank >= world) return B2C_ERR_INVALID;
   DevGuard g(c->dev);
-  int rc = seam_alloc(c);
-  if (rc != B2C_OK) return rc;
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->s_main;
+  if (c->hyst_phase_timing) { cudaEventRecord(c->ev_s[3], st); cudaEventRecord(c->ev_s[4], st); }
   const uint32_t *recs[b2c::SEAM_MAXW];
   const size_t stride = b2c::seam_rec_words(c->wpr);
   for (int r = 0; r < world; ++r) recs[r] = (const uint32_t *)all_records_dev + (size_t)r * stride;
-  return seam_solve(c, recs, world, rank, stream ? (cudaStream_t)stream : c->s_main);
+  return seam_solve(c, recs, world, rank, nullptr, st);
 }
 
 int b2c_band_status(b2c_handle c, int *promoted_runs, int *error)
 {
   if (!c || !c->band) return B2C_ERR_INVALID;
   DevGuard g(c->dev);
-  if (!c->d_seam_ctl) {
-    if (promoted_runs) *promoted_runs = 0;
-    if (error) *error = 0;
-    return B2C_OK;
-  }
-  CK(c, cudaMemcpyAsync(c->h_seam_ctl, c->d_seam_ctl, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->s_main));
-  CK(c, cudaStreamSynchronize(c->s_main));
+  CK(c, cudaDeviceSynchronize());   // the band's work may be on any stream
+  CK(c, cudaMemcpy(c->h_seam_ctl, c->d_seam_ctl, 8 * sizeof(int), cudaMemcpyDeviceToHost));
   if (promoted_runs) *promoted_runs = c->h_seam_ctl[3];
   if (error) *error = c->h_seam_ctl[2];
   return B2C_OK;
@@ -1033,9 +1103,7 @@ int p2p_alloc(b2c_ctx *c)
   CK(c, cudaMalloc(&c->d_mailbox, bytes));
   CK(c, cudaMemset(c->d_mailbox, 0, bytes));
   void *in;
-  int rc = b2c_band_input(c, &in, nullptr);
-  if (rc != B2C_OK) return rc;
-  return seam_alloc(c);
+  return b2c_band_input(c, &in, nullptr);
 }
 }// namespace
 
@@ -1133,65 +1201,62 @@ void fill_p2p(b2c_ctx *c, b2c::B2cBandP2P &q)
 }
 }// namespace
 
-// the 4 input rows on either side of every seam, stored straight into the neighbours' band input buffers; returns
-// (asynchronously) once both neighbours' rows have landed in this band's buffer.  phase: B2C_P2P_ALL, or B2C_P2P_PUSH
-// then B2C_P2P_WAIT (a single-process driver of several bands issues ALL pushes before the first wait: a device-side
-// wait must never be queued ahead of the store it waits for).
-int b2c_band_p2p_halo(b2c_handle c, void *stream, int phase)
+// Stencil of the band in the handle's own input buffer (b2c_band_input) with the halo exchange over peer memory hidden
+// behind it: my first / last 4 rows are stored into the neighbours' buffers, the rows that need no halo (all but the
+// first / last 4 of a band with a neighbour on that side) are computed, and only the 4-row strips next to a seam wait for
+// the neighbours' rows.  phase: B2C_P2P_ALL, or B2C_P2P_PUSH (push + interior rows) then B2C_P2P_WAIT (wait + strips): a
+// single-process driver of several bands issues ALL pushes before the first wait -- a device-side wait must never be
+// queued ahead of the store it waits for.
+int b2c_band_p2p_stencil(b2c_handle c, void *stream, int phase)
 {
   if (!c || !c->band || c->p2p_world < 2 || !c->d_band_in || phase < B2C_P2P_ALL || phase > B2C_P2P_WAIT) return B2C_ERR_INVALID;
   DevGuard g(c->dev);
   cudaStream_t st = stream ? (cudaStream_t)stream : c->s_main;
   b2c::B2cBandP2P q;
   fill_p2p(c, q);
-  const int cpr = (c->w * 3 + 15) / 16, nblocks = (4 * cpr + 255) / 256;
+  const size_t stride = (size_t)q.in_stride;
+  const uint8_t *row0 = c->d_band_in + 4 * stride;
+  const int rows = c->rows_alloc, cpr = (c->w * 3 + 15) / 16, nblocks = (4 * cpr + 255) / 256;
+  const bool up = c->p2p_rank > 0, dn = c->p2p_rank < c->p2p_world - 1;
+  // rows [i0, i1) need no halo row; a band of fewer than 8 rows between two seams has none
+  const int i0 = up ? 4 : 0, i1 = std::max(i0, dn ? rows - 4 : rows);
+  int rc = B2C_OK;
+  const bool pt = c->hyst_phase_timing;
   if (phase != B2C_P2P_WAIT) {
+    if (pt) cudaEventRecord(c->ev_b[0], st);
     c->p2p_run += 1;
     CK(c, cudaMemsetAsync(c->d_seam_ctl + 2, 0, sizeof(int), st));   // a time-out of an earlier run is not sticky
     b2c::k_band_push_halo<<<dim3(nblocks, 2), 256, 0, st>>>(q);
     c->launches++;
+    rc = launch_stencil_rows(c, row0, stride, i0, i1 - i0, st);
+    if (rc != B2C_OK) return rc;
+    if (pt) cudaEventRecord(c->ev_b[1], st);
   }
   if (phase != B2C_P2P_PUSH) {
     b2c::k_band_wait_halo<<<1, 1, 0, st>>>(q, c->p2p_run, nblocks);
     c->launches++;
+    if (pt) cudaEventRecord(c->ev_b[2], st);
+    if (up) rc = launch_stencil_rows(c, row0, stride, 0, std::min(i0, rows), st);
+    if (rc == B2C_OK && dn && i1 < rows) rc = launch_stencil_rows(c, row0, stride, std::max(i1, i0), rows - std::max(i1, i0), st);
+    if (pt) cudaEventRecord(c->ev_b[3], st);
   }
   CK(c, cudaGetLastError());
-  return B2C_OK;
+  return rc;
 }
 
-// cross-band hysteresis over peer memory: my seam record -> every rank's mailbox, wait for all records, solve, resolve.
-// Asynchronous on `stream`; b2c_band_status reports a peer time-out.  phase as above.
-int b2c_band_p2p_seam(b2c_handle c, void *stream, int phase)
+// cross-band hysteresis over peer memory, after b2c_band_hysteresis (which published and pushed my record): wait for all
+// records, solve, promote.  Asynchronous on `stream`; b2c_band_status reports a peer time-out.
+int b2c_band_p2p_seam(b2c_handle c, void *stream)
 {
-  if (!c || !c->band || c->p2p_world < 2 || !c->d_mailbox || phase < B2C_P2P_ALL || phase > B2C_P2P_WAIT) return B2C_ERR_INVALID;
+  if (!c || !c->band || c->p2p_world < 2 || !c->d_mailbox) return B2C_ERR_INVALID;
   DevGuard g(c->dev);
   cudaStream_t st = stream ? (cudaStream_t)stream : c->s_main;
-  const int world = c->p2p_world, rank = c->p2p_rank;
-  uint32_t *mine = (uint32_t *)c->peer_mail[rank];
-  if (phase != B2C_P2P_WAIT) {
-    const int par = (c->seam_run + 1) & 1;   // seam_publish increments seam_run
-    int rc = seam_publish(c, mine + b2c::bp_seam_slot(c->wpr, par, rank), st);
-    if (rc != B2C_OK) return rc;
-    b2c::B2cSeamPeers q;
-    memset(&q, 0, sizeof(q));
-    for (int k = 0; k < world; ++k) {
-      q.slot[k] = (uint32_t *)c->peer_mail[k] + b2c::bp_seam_slot(c->wpr, par, rank);
-      q.flag[k] = (uint32_t *)c->peer_mail[k] + b2c::bp_seam_flag(c->wpr, par, rank);
-    }
-    q.world = world;
-    q.rank = rank;
-    b2c::k_seam_push<<<world, b2c::SEAM_THREADS, 0, st>>>(q, c->wpr, c->seam_run);
-    CK(c, cudaGetLastError());
-    c->launches++;
-  }
-  if (phase == B2C_P2P_PUSH) return B2C_OK;
-  const int par = c->seam_run & 1;
-  b2c::k_seam_wait<<<1, 32, 0, st>>>(mine + b2c::bp_seam_flag(c->wpr, par, 0), world, c->seam_run, c->d_seam_ctl);
-  CK(c, cudaGetLastError());
-  c->launches++;
+  const int world = c->p2p_world, rank = c->p2p_rank, par = c->seam_run & 1;
+  uint32_t *mine = own_mail(c);
+  if (c->hyst_phase_timing) cudaEventRecord(c->ev_s[4], st);
   const uint32_t *recs[b2c::SEAM_MAXW];
   for (int r = 0; r < world; ++r) recs[r] = mine + b2c::bp_seam_slot(c->wpr, par, r);
-  return seam_solve(c, recs, world, rank, st);
+  return seam_solve(c, recs, world, rank, mine + b2c::bp_seam_flag(c->wpr, par, 0), st);   // (the solve kernel waits for the flags)
 }
 
 // ---- misc -----------------------------------------------------------------------------------------
@@ -1239,6 +1304,10 @@ int b2c_set_option(b2c_handle c, const char *name, int value)
       for (auto &e : c->ev_h) CK(c, cudaEventCreate(&e));
     return B2C_OK;
   }
+  if (!strcmp(name, "seam_force_global")) {
+    c->seam_force_global = value != 0;
+    return B2C_OK;
+  }
   if (!strcmp(name, "march_extra_smem")) {
     if (value < 0 || value > 64 * 1024) return B2C_ERR_INVALID;
     c->march_extra_smem = value;
@@ -1254,6 +1323,20 @@ int b2c_set_option(b2c_handle c, const char *name, int value)
 int b2c_get_info(b2c_handle c, const char *name)
 {
   if (!c || !name) return B2C_ERR_INVALID;
+  if (!strncmp(name, "band_stencil_us", 15)) {   // b2c_band_p2p_stencil with "hyst_phase_timing": push + interior rows, wait, seam strips (us)
+    const int k = name[15] - '0';
+    if (k < 0 || k > 2 || !c->ev_b[0]) return B2C_ERR_INVALID;
+    float ms = 0;
+    if (cudaEventSynchronize(c->ev_b[3]) != cudaSuccess || cudaEventElapsedTime(&ms, c->ev_b[k], c->ev_b[k + 1]) != cudaSuccess) return B2C_ERR_CUDA;
+    return (int)(ms * 1000.0f + 0.5f);
+  }
+  if (!strncmp(name, "seam_phase_us", 13)) {   // band mode with "hyst_phase_timing": tile+border, publish(+push), resolve, wait, solve, list pass (us)
+    const int k = name[13] - '0';
+    if (k < 0 || k > 5 || !c->ev_s[0]) return B2C_ERR_INVALID;
+    float ms = 0;
+    if (cudaEventSynchronize(c->ev_s[6]) != cudaSuccess || cudaEventElapsedTime(&ms, c->ev_s[k], c->ev_s[k + 1]) != cudaSuccess) return B2C_ERR_CUDA;
+    return (int)(ms * 1000.0f + 0.5f);
+  }
   if (!strncmp(name, "hyst_phase_us", 13)) {   // phase times of the last union-find hysteresis run with "hyst_phase_timing" on (us)
     const int k = name[13] - '0';
     if (k < 0 || k > 2 || !c->ev_h[0]) return B2C_ERR_INVALID;

@@ -38,13 +38,17 @@ __device__ __forceinline__ int uf_find(int *P, int n)
 
 // find for the resolve phase: no union runs concurrently any more, so every value ever stored in P[n-1] is an
 // ancestor of n and plain stores are enough for the compression (no atomic round trip on the critical path).
+// Row bands: k_seam_publish TAGS the roots of the components that reach the band's first or last row (sign bit of the
+// root's own entry, UF_TAG); such a root is returned with its tag (a negative number), every other root as itself.
+constexpr int UF_TAG = (int)0x80000000u;
 __device__ __forceinline__ int uf_find_final(int *P, int n)
 {
   while (n != 0) {
     const int pn = __ldcg(P + n - 1);
-    if (pn == n || pn == 0) return pn;
+    if (pn == n || pn <= 0) return pn;
     const int gp = __ldcg(P + pn - 1);
     if (gp == pn) return pn;
+    if (gp < 0) return gp;
     __stcg(P + n - 1, gp);
     n = gp;
   }
@@ -319,9 +323,10 @@ __global__ void __launch_bounds__(UFK_THREADS) k_uf_border(const B2cHystParams p
 // Body for one plane word; returns true if the word gained edge bits.
 // (s, c = the word's S and C values, already loaded: lets a caller keep many loads in flight)
 template <bool EXPAND, bool ONLY_CHANGED = false>
-__device__ __forceinline__ bool uf_resolve_expand_word_sc(const B2cHystParams &p, int f, int y, int xw, int W32, uint32_t s, const uint32_t c)
+__device__ __forceinline__ bool uf_resolve_expand_word_sc(const B2cHystParams &p, int f, int y, int xw, int W32, uint32_t s, const uint32_t c, int *left_root = nullptr)
 {
   bool changed = false;
+  int nleft = 0, lroot = 0;
   const long long o = f * p.plane_frame_stride + (long long)y * p.plane_pitch + xw;
   uint32_t m = c & ~s;
   if (m) {
@@ -332,13 +337,16 @@ __device__ __forceinline__ bool uf_resolve_expand_word_sc(const B2cHystParams &p
       const uint32_t lo = m & (0u - m);
       const uint32_t run = m & ~(m + lo);
       m &= ~run;
-      if (uf_find_final(P, base + __ffs((int)lo) - 1) == 0) add |= run;
+      const int root = uf_find_final(P, base + __ffs((int)lo) - 1);
+      if (root == 0) add |= run;
+      else if (root < 0) { lroot = nleft ? -1 : (root & ~UF_TAG); ++nleft; }   // (an untagged root can never be promoted)
     }
     if (add) {
       s |= add;
       changed = true;
     }
   }
+  if (left_root) *left_root = lroot;          // row bands, runs under TAGGED roots: 0 = none, > 0 = the root of the only one, -1 = several
   if (!ONLY_CHANGED || changed) p.E[o] = s;   // E = edges: strong | promoted weak (S itself stays what the stencil wrote)
   if (EXPAND && (!ONLY_CHANGED || changed)) {   // (ONLY_CHANGED: the map already holds the previous state of every word)
     uint8_t *out = p.edges + f * p.edges_frame_stride + (long long)y * p.edges_pitch + xw * 32;
@@ -369,25 +377,64 @@ __device__ __forceinline__ bool uf_resolve_expand_word(const B2cHystParams &p, i
 
 // One thread per plane word of TWO rows (both rows' loads in flight before either is looked at): block =
 // (blockDim.x words) x (2 * blockDim.y rows); grid: x = word blocks of a row, y = row blocks, z = frame.
-template <bool EXPAND, bool ONLY_CHANGED = false>
-__global__ void __launch_bounds__(UFK_THREADS) k_uf_resolve(const B2cHystParams p, int *bcount)
+// LIST (row bands, one frame): the words with unresolved weak runs whose component reaches the band's first or last row
+// (tagged roots) are appended to ulist as (word index y * pitch + xw, root of the word's one such run -- or 0 if it has
+// several); *ucount may exceed ucap = overflow.  Only these can still be promoted by the seam solve, and
+// k_uf_resolve_list then visits these words only.
+template <bool EXPAND, bool LIST = false>
+__global__ void __launch_bounds__(UFK_THREADS) k_uf_resolve(const B2cHystParams p, int *bcount, uint2 *ulist = nullptr, int *ucount = nullptr, const int ucap = 0)
 {
-  if ((p.skip && __ldcg(p.skip)) || (p.need && __ldcg(p.need) == 0)) return;
+  if (p.skip && __ldcg(p.skip)) return;
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) bcount[blockIdx.z] = 0;   // the border list of this frame is consumed
   const int wpr = (p.w + 31) >> 5, W32 = p.plane_pitch * 32;
   const int xw = blockIdx.x * blockDim.x + threadIdx.x, y = 2 * (blockIdx.y * blockDim.y + threadIdx.y), f = blockIdx.z;
-  bool changed = false;
+  int left0 = 0, left1 = 0;
   if (xw < wpr && y < p.h) {
     const long long o = f * p.plane_frame_stride + (long long)y * p.plane_pitch + xw;
     const bool two = y + 1 < p.h;
-    const uint32_t *cur = ONLY_CHANGED ? p.E : p.S;   // first pass: from the stencil's S plane; re-pass (row bands): from the edges so far
-    const uint32_t s0 = cur[o], c0 = p.C[o], s1 = two ? cur[o + p.plane_pitch] : 0u, c1 = two ? p.C[o + p.plane_pitch] : 0u;
-    changed = uf_resolve_expand_word_sc<EXPAND, ONLY_CHANGED>(p, f, y, xw, W32, s0, c0);
-    if (two) changed |= uf_resolve_expand_word_sc<EXPAND, ONLY_CHANGED>(p, f, y + 1, xw, W32, s1, c1);
+    const uint32_t s0 = p.S[o], c0 = p.C[o], s1 = two ? p.S[o + p.plane_pitch] : 0u, c1 = two ? p.C[o + p.plane_pitch] : 0u;
+    uf_resolve_expand_word_sc<EXPAND>(p, f, y, xw, W32, s0, c0, &left0);
+    if (two) uf_resolve_expand_word_sc<EXPAND>(p, f, y + 1, xw, W32, s1, c1, &left1);
   }
-  // a plain store, and only while the flag is still clear (a same-address atomic per thread serialises in L2 and cost
-  // more than the whole phase)
-  if (changed && __ldcg(p.flags + 4) == 0) __stcg(p.flags + 4, 1);
+  if (LIST) {   // warp-aggregated append (blockDim.x is a multiple of 32: a warp is 32 consecutive words of one row pair)
+    const unsigned m0 = __ballot_sync(B2C_FULL, left0 != 0), m1 = __ballot_sync(B2C_FULL, left1 != 0);
+    const int n0 = __popc(m0), n = n0 + __popc(m1);
+    if (n) {
+      const int lane = threadIdx.x & 31;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(ucount, n);
+      base = __shfl_sync(B2C_FULL, base, 0);
+      const unsigned lt = (1u << lane) - 1u;
+      const int i0 = base + __popc(m0 & lt), i1 = base + n0 + __popc(m1 & lt);
+      if (left0 && i0 < ucap) ulist[i0] = make_uint2((uint32_t)(y * p.plane_pitch + xw), (uint32_t)max(left0, 0));
+      if (left1 && i1 < ucap) ulist[i1] = make_uint2((uint32_t)((y + 1) * p.plane_pitch + xw), (uint32_t)max(left1, 0));
+    }
+  }
+}
+
+// Row bands, after the seam solve hung this band's promoted roots under node 0: the listed words again -- one load of
+// the recorded root's parent decides a word with one unresolved run -- or, if the list overflowed, every word of the
+// band; only words that gain edge pixels are rewritten (E plane and u8 map).
+template <bool EXPAND>
+__global__ void __launch_bounds__(UFK_THREADS) k_uf_resolve_list(const B2cHystParams p, const uint2 *ulist, const int *ucount, const int ucap, const int *need)
+{
+  if (need && __ldcg(need) == 0) return;
+  const int wpr = (p.w + 31) >> 5, W32 = p.plane_pitch * 32, n = __ldcg(ucount);
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  if (n <= ucap) {
+    for (int i = tid; i < n; i += nt) {
+      const uint2 e = ulist[i];
+      if (e.y != 0u && __ldcg(p.parent + e.y - 1) != 0) continue;   // its component was not promoted
+      const int wi = (int)e.x, y = wi / p.plane_pitch, xw = wi - y * p.plane_pitch;
+      uf_resolve_expand_word_sc<EXPAND, true>(p, 0, y, xw, W32, p.E[wi], p.C[wi]);
+    }
+  } else {
+    for (int i = tid; i < p.h * wpr; i += nt) {
+      const int y = i / wpr, xw = i - y * wpr;
+      const long long o = (long long)y * p.plane_pitch + xw;
+      uf_resolve_expand_word_sc<EXPAND, true>(p, 0, y, xw, W32, p.E[o], p.C[o]);
+    }
+  }
 }
 
 // expand: S plane -> u8 {0,255}; one thread per 16 pixels (one 128-bit store)

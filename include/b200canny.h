@@ -131,41 +131,47 @@ B2C_API void *b2c_stream(b2c_handle h);
  * (unless the band starts at global row 0) and the 4 rows below it (unless it ends at the last global row): the
  * stencil needs 2 (Gaussian) + 1 (Sobel) + 1 (NMS) neighbour rows, and uses the reference's zero padding only outside
  * the global image.  Per image: [halo exchange] -> b2c_band_stencil -> b2c_band_hysteresis (band-local fixpoint, planes
- * and union-find forest are kept) -> ONE exchange of seam records -> solve; the result equals the unsharded run bit
- * for bit.  All calls are asynchronous on `stream`. */
+ * and union-find forest are kept, the band's seam record is built) -> ONE exchange of seam records -> solve; the result
+ * equals the unsharded run bit for bit.  All calls are asynchronous on `stream`. */
 B2C_API int b2c_create_band(b2c_handle *out, int device, int width, int band_rows, int y0, int height_global);
 B2C_API int b2c_band_stencil(b2c_handle h, const uint8_t *dev_bgr_band_row0, size_t row_stride, void *stream);
 B2C_API int b2c_band_hysteresis(b2c_handle h, void *stream);
-/* Cross-band hysteresis in one step.  Every band publishes its SEAM RECORD (b2c_band_seam_bytes bytes: the edge and
- * unresolved-weak bit rows of its first and last row + a component label per unresolved run), the caller all-gathers
- * the records of all bands in band order (any transport: NCCL, MPI, a memcpy), and every band solves the same small
- * connected-components problem over all seams and promotes its own components that reach an edge pixel of any band.
- * b2c_band_seam_publish: *record_dev = device address of this band's record (owned by the handle);
+/* Cross-band hysteresis in one step.  b2c_band_hysteresis leaves the band's SEAM RECORD (b2c_band_seam_bytes bytes: the
+ * edge and unresolved-weak bit rows of its first and last row + a component label per unresolved run) in device memory;
+ * the caller all-gathers the records of all bands in band order (any transport: NCCL, MPI, a memcpy), and every band
+ * solves the same small connected-components problem over all seams and promotes its own components that reach an edge
+ * pixel of any band (only the plane words that were still unresolved are visited again).
+ * b2c_band_seam_record: *record_dev = device address of this band's record (owned by the handle, rewritten by every
+ * b2c_band_hysteresis on its stream);
  * b2c_band_seam_solve: all_records_dev = world records, b2c_band_seam_bytes apart. */
 B2C_API int b2c_band_seam_bytes(b2c_handle h, size_t *bytes);
-B2C_API int b2c_band_seam_publish(b2c_handle h, void **record_dev, void *stream);
+B2C_API int b2c_band_seam_record(b2c_handle h, void **record_dev);
 B2C_API int b2c_band_seam_solve(b2c_handle h, const void *all_records_dev, int world, int rank, void *stream);
-/* blocking: weak runs of this band promoted by the last solve, and whether a peer-to-peer wait timed out */
+/* blocking (synchronises the device): weak runs of this band promoted by the last solve, and whether a peer-to-peer
+ * wait timed out */
 B2C_API int b2c_band_status(b2c_handle h, int *promoted_runs, int *error);
 
 /* Peer-to-peer transport for ranks of ONE box: every rank maps the other ranks' mailboxes and band input buffers
  * (CUDA IPC between processes: export a 144-byte blob, all-gather the blobs, open; or b2c_band_p2p_open_local for
  * bands of one process) and the halo rows and seam records travel as ordinary stores over NVLink, with flag words
- * instead of collectives.
+ * instead of collectives, hidden behind the band's own work:
  * b2c_band_input: the band's input buffer owned by the handle (so that it can be shared): rows 0..3 = halo rows above
- * the band, rows 4..4+band_rows-1 = the band, then 4 halo rows; rows are row_stride bytes apart;
- * b2c_band_p2p_halo: my first / last 4 rows -> the neighbours' buffers; later work on `stream` sees both neighbours' rows;
- * b2c_band_p2p_seam: publish + all-gather over peer memory + solve (replaces the publish / gather / solve calls above).
+ *   the band, rows 4..4+band_rows-1 = the band, then 4 halo rows; rows are row_stride bytes apart;
+ * b2c_band_p2p_stencil: stencil of the band in that buffer: my first / last 4 rows -> the neighbours' buffers, the rows
+ *   that need no halo are computed meanwhile, only the 4-row strips at the seams wait for the neighbours' rows;
+ * b2c_band_hysteresis (on a wired handle): also stores the seam record into every rank's mailbox before it resolves;
+ * b2c_band_p2p_seam: waits for all records, solves, promotes (replaces the gather + b2c_band_seam_solve above).
  * phase: B2C_P2P_ALL for a rank that drives one band.  A process that drives SEVERAL bands (b2c_band_p2p_open_local)
- * gives every band its own stream and calls B2C_P2P_PUSH for all bands before B2C_P2P_WAIT for any: the waits spin on the
- * device and must never be queued ahead of the stores they wait for.  Every wait has a 2 s time-out (b2c_band_status). */
+ * gives every band its own stream and issues, band by band, b2c_band_p2p_stencil(PUSH), then (WAIT), then
+ * b2c_band_hysteresis, then b2c_band_p2p_seam: the waits spin on the device and must never be queued ahead of the
+ * stores they wait for.  Every wait has a 2 s time-out (b2c_band_status reports it, the next run clears it). */
 enum { B2C_P2P_ALL = 0, B2C_P2P_PUSH = 1, B2C_P2P_WAIT = 2 };
 B2C_API int b2c_band_input(b2c_handle h, void **dev_ptr, size_t *row_stride);
 B2C_API int b2c_band_p2p_export(b2c_handle h, void *blob_144);
 B2C_API int b2c_band_p2p_open(b2c_handle h, const void *all_blobs, int world, int rank);
 B2C_API int b2c_band_p2p_open_local(b2c_handle h, const b2c_handle *all_handles, int world, int rank);
-B2C_API int b2c_band_p2p_halo(b2c_handle h, void *stream, int phase);
-B2C_API int b2c_band_p2p_seam(b2c_handle h, void *stream, int phase);
+B2C_API int b2c_band_p2p_stencil(b2c_handle h, void *stream, int phase);
+B2C_API int b2c_band_p2p_seam(b2c_handle h, void *stream);
 
 /* ---- misc */
 B2C_API const char *b2c_strerror(int status);
@@ -175,10 +181,12 @@ B2C_API int b2c_device_count(void);
 /* kernels launched by this handle since creation (bench.py reports it as gpu_launches) */
 B2C_API long long b2c_launch_count(b2c_handle h);
 /* options: "stencil_impl" 0 = marching kernel (default), 1 = staged tile kernel (the all-stages path of the
- * accessors); "march_rb" rows per band of the marching kernel (0 = automatic); "hyst_phase_timing"; "uf_spread" */
+ * accessors); "march_rb" rows per band of the marching kernel (0 = automatic); "hyst_phase_timing"; "uf_spread";
+ * "seam_force_global" (tests: the large-seam code paths of the seam kernels) */
 B2C_API int b2c_set_option(b2c_handle h, const char *name, int value);
 /* read-only facts: "sm_count", "stencil_impl", "march_ctas_per_sm", "march_band_rows", "in_row_stride",
- * "plane_pitch_words", "map_pitch_words", "hyst_phase_us0..2" */
+ * "plane_pitch_words", "map_pitch_words", "hyst_phase_us0..2", "seam_phase_us0..5" and "band_stencil_us0..2"
+ * (band handles) */
 B2C_API int b2c_get_info(b2c_handle h, const char *name);
 
 /* ---- deterministic synthetic frames (host side; identical to cudacam_b200/synth.py).

@@ -156,16 +156,35 @@ __attribute__((visibility("default"))) int emu_hysteresis(const uint32_t *map2, 
 }
 
 // ---- one row band with retained planes and forest (row-band protocol on the CPU) ---------------------------------------
+// Same launch order as b2c_band_hysteresis / b2c_band_seam_solve: tile, border, publish, resolve<LIST> | solve, list pass.
 struct EmuBand {
   EmuPlanes P;
   std::vector<uint8_t> edges;
-  std::vector<int> roots, hkey, hval, sP, pre;
+  std::vector<int> roots, hkey, hval, sP;
+  std::vector<uint2> ulist;
+  std::vector<uint32_t> rec;
+  bool force_global = false;
+  int ucap = 0;
   int ctl[8] = { 0 };
   int run = 0;
 };
-__attribute__((visibility("default"))) void *emu_band_create(int w, int h)
+constexpr int EMU_SEAM_THREADS = 128;   // (the kernels take the CTA size from blockDim; 1024 OS threads per block would be slow)
+static b2c::B2cSeamBand emu_seam_band(EmuBand *b)
+{
+  b2c::B2cSeamBand s;
+  s.S = b->P.S.data() + b->P.pitch; s.C = b->P.C.data() + b->P.pitch;
+  s.plane_pitch = b->P.pitch; s.wpr = b->P.wpr; s.h = b->P.h;
+  s.parent = b->P.parent.data(); s.roots = b->roots.data(); s.hkey = b->hkey.data(); s.hval = b->hval.data();
+  s.hsize = (int)b->hkey.size(); s.ctl = b->ctl;
+  s.shash = b->force_global ? 0 : b2c::SEAM_SHASH; s.snodes = b->force_global ? 0 : b2c::SEAM_SNODES;
+  return s;
+}
+// ucap: capacity of the unresolved-word list (<= 0: the product's sizing); a tiny one exercises the overflow path
+// force_global: global-memory hash / forest in the seam kernels (the product takes them for very busy seams only)
+__attribute__((visibility("default"))) void *emu_band_create(int w, int h, int ucap, int force_global)
 {
   EmuBand *b = new EmuBand;
+  b->force_global = force_global != 0;
   b->P.init(w, h, 1);
   b->edges.assign((size_t)w * h, 0);
   const int cap = b2c::seam_cap(b->P.wpr), hs = b2c::seam_hash_size(b->P.wpr);
@@ -173,33 +192,39 @@ __attribute__((visibility("default"))) void *emu_band_create(int w, int h)
   b->hkey.assign(hs, 0);
   b->hval.assign(hs, 0);
   b->sP.assign((size_t)b2c::SEAM_MAXW * 2 * cap + 1, 0);
-  b->pre.assign((size_t)b2c::SEAM_MAXW * 2 * b->P.wpr, 0);
+  b->rec.assign(b2c::seam_rec_words(b->P.wpr), 0u);
+  b->ucap = ucap > 0 ? ucap : std::max(4096, b->P.wpr * h / 4);
+  b->ulist.assign(b->ucap, uint2{ 0u, 0u });
   return b;
 }
 __attribute__((visibility("default"))) void emu_band_destroy(void *h) { delete static_cast<EmuBand *>(h); }
 __attribute__((visibility("default"))) int emu_seam_words(int w) { return (int)b2c::seam_rec_words((w + 31) / 32); }
-__attribute__((visibility("default"))) void emu_band_hysteresis(void *h, const uint32_t *map2)
+// band-local hysteresis; the seam record is copied to rec_out
+__attribute__((visibility("default"))) void emu_band_hysteresis(void *h, const uint32_t *map2, uint32_t *rec_out)
 {
   EmuBand *b = static_cast<EmuBand *>(h);
-  b->P.from_map2(map2);
-  b->P.hysteresis(b->edges.data());
-}
-static b2c::B2cSeamBand emu_seam_band(EmuBand *b)
-{
-  b2c::B2cSeamBand s;
-  s.S = b->P.E.data() + b->P.pitch; s.C = b->P.C.data() + b->P.pitch;
-  s.plane_pitch = b->P.pitch; s.wpr = b->P.wpr; s.h = b->P.h;
-  s.parent = b->P.parent.data(); s.roots = b->roots.data(); s.hkey = b->hkey.data(); s.hval = b->hval.data();
-  s.hsize = (int)b->hkey.size(); s.ctl = b->ctl;
-  return s;
-}
-constexpr int EMU_SEAM_THREADS = 128;   // (the kernels take the CTA size from blockDim; 1024 OS threads per block would be slow)
-__attribute__((visibility("default"))) void emu_band_publish(void *h, uint32_t *rec)
-{
-  EmuBand *b = static_cast<EmuBand *>(h);
+  EmuPlanes &P = b->P;
+  P.from_map2(map2);
+  const B2cHystParams p = P.params(b->edges.data());
+  const dim3 gt((P.wpr + b2c::UT_WORDS - 1) / b2c::UT_WORDS, (P.h + b2c::UT_ROWS - 1) / b2c::UT_ROWS, 1);
+  uint32_t *blp = P.bl.data();
+  int *bcp = P.bc.data();
+  const int cap = P.bcap;
+  emu::launch(gt, dim3(b2c::UT_THREADS), b2c::UT_SMEM, false, [=] { b2c::k_uf_tile(p, blp, bcp, cap); });
+  emu::launch(dim3(2, 1, 1), dim3(b2c::UFK_THREADS), 0, false, [=] { b2c::k_uf_border(p, blp, bcp, cap); });
   const b2c::B2cSeamBand s = emu_seam_band(b);
   const int run = ++b->run;
-  emu::launch(dim3(1), dim3(EMU_SEAM_THREADS), b2c::seam_smem_bytes(b->P.wpr), false, [=] { b2c::k_seam_publish(s, rec, run); });
+  uint32_t *rec = b->rec.data();
+  b2c::B2cSeamPeers q;
+  memset(&q, 0, sizeof(q));
+  emu::launch(dim3(1), dim3(EMU_SEAM_THREADS), b2c::seam_publish_smem(P.wpr), false, [=] { b2c::k_seam_publish(s, rec, run, q); });
+  const int tx = 32, ty = 4;
+  const dim3 gr((P.wpr + tx - 1) / tx, (P.h + 2 * ty - 1) / (2 * ty), 1), br(tx, ty);
+  uint2 *ul = b->ulist.data();
+  int *uc = b->ctl + 4;
+  const int ucap = b->ucap;
+  emu::launch(gr, br, 0, false, [=] { b2c::k_uf_resolve<true, true>(p, bcp, ul, uc, ucap); });
+  memcpy(rec_out, rec, b->rec.size() * 4);
 }
 __attribute__((visibility("default"))) int emu_band_solve(void *h, const uint32_t *all_records, int world, int rank)
 {
@@ -209,16 +234,16 @@ __attribute__((visibility("default"))) int emu_band_solve(void *h, const uint32_
   memset(&a, 0, sizeof(a));
   const size_t stride = b2c::seam_rec_words(b->P.wpr);
   for (int r = 0; r < world; ++r) a.rec[r] = all_records + r * stride;
-  a.world = world; a.rank = rank; a.P = b->sP.data(); a.pre = b->pre.data();
-  emu::launch(dim3(1), dim3(EMU_SEAM_THREADS), b2c::seam_smem_bytes(b->P.wpr), false, [=] { b2c::k_seam_solve(s, a); });
-  B2cHystParams p = b->P.params(b->edges.data());
-  p.need = b->ctl;
-  int *bcp = b->P.bc.data();
-  const int tx = 32, ty = 4;
-  const dim3 gr((b->P.wpr + tx - 1) / tx, (b->P.h + 2 * ty - 1) / (2 * ty), 1), br(tx, ty);
-  emu::launch(gr, br, 0, false, [=] { b2c::k_uf_resolve<true, true>(p, bcp); });
+  a.world = world; a.rank = rank; a.P = b->sP.data();
+  emu::launch(dim3(1), dim3(EMU_SEAM_THREADS), b2c::seam_solve_smem(), false, [=] { b2c::k_seam_solve(s, a); });
+  const B2cHystParams p = b->P.params(b->edges.data());
+  const uint2 *ul = b->ulist.data();
+  const int *uc = b->ctl + 4, *need = b->ctl;
+  const int ucap = b->ucap;
+  emu::launch(dim3(3), dim3(b2c::UFK_THREADS), 0, false, [=] { b2c::k_uf_resolve_list<true>(p, ul, uc, ucap, need); });
   return b->ctl[3];
 }
+__attribute__((visibility("default"))) int emu_band_unresolved_words(void *h) { return static_cast<EmuBand *>(h)->ctl[4]; }
 __attribute__((visibility("default"))) void emu_band_edges(void *h, uint8_t *out)
 {
   EmuBand *b = static_cast<EmuBand *>(h);

@@ -37,15 +37,15 @@ def lib():
         _lib.emu_hysteresis.restype = _i
         _lib.emu_hysteresis.argtypes = [_vp, _i, _i, _i, _vp, _vp]
         _lib.emu_band_create.restype = _vp
-        _lib.emu_band_create.argtypes = [_i, _i]
+        _lib.emu_band_create.argtypes = [_i, _i, _i, _i]
         _lib.emu_band_destroy.restype = None
         _lib.emu_band_destroy.argtypes = [_vp]
         _lib.emu_seam_words.restype = _i
         _lib.emu_seam_words.argtypes = [_i]
         _lib.emu_band_hysteresis.restype = None
-        _lib.emu_band_hysteresis.argtypes = [_vp, _vp]
-        _lib.emu_band_publish.restype = None
-        _lib.emu_band_publish.argtypes = [_vp, _vp]
+        _lib.emu_band_hysteresis.argtypes = [_vp, _vp, _vp]
+        _lib.emu_band_unresolved_words.restype = _i
+        _lib.emu_band_unresolved_words.argtypes = [_vp]
         _lib.emu_band_solve.restype = _i
         _lib.emu_band_solve.argtypes = [_vp, _vp, _i, _i]
         _lib.emu_band_edges.restype = None
@@ -82,10 +82,11 @@ def stencil(bgr, lo=10, hi=40, impl=1, stages=False, y0=0, h_glob=None, rows=Non
 class Band:
     """One row band with retained planes and union-find forest (the emulated twin of a b2c band handle)."""
 
-    def __init__(self, w, h):
+    def __init__(self, w, h, ucap=0, force_global=False):
         self.w, self.h = w, h
-        self._h = lib().emu_band_create(w, h)
+        self._h = lib().emu_band_create(w, h, ucap, 1 if force_global else 0)
         self.seam_words = lib().emu_seam_words(w)
+        self.record = np.zeros(self.seam_words, np.uint32)
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -93,13 +94,12 @@ class Band:
             self._h = None
 
     def hysteresis(self, map2):
+        """Band-local pass; leaves the seam record in self.record."""
         m = np.ascontiguousarray(map2, np.uint32)
-        lib().emu_band_hysteresis(self._h, m.ctypes.data)
+        lib().emu_band_hysteresis(self._h, m.ctypes.data, self.record.ctypes.data)
 
-    def publish(self):
-        rec = np.zeros(self.seam_words, np.uint32)
-        lib().emu_band_publish(self._h, rec.ctypes.data)
-        return rec
+    def unresolved_words(self):
+        return lib().emu_band_unresolved_words(self._h)
 
     def solve(self, all_records, world, rank):
         a = np.ascontiguousarray(all_records, np.uint32)

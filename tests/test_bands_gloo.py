@@ -19,11 +19,11 @@ from cudacam_b200 import bands, synth
 class EmuBandBackend:
     """Same interface as bands.CudaBandBackend; pixel work by the emulated kernels (test-only)."""
 
-    def __init__(self, width, rows, y0, height_global, thresh_override=None):
+    def __init__(self, width, rows, y0, height_global, thresh_override=None, ucap=0, force_global=False):
         self.width, self.rows, self.y0, self.height_global = width, rows, y0, height_global
         self.row_stride = (width * 3 + 15) // 16 * 16
         self.buf = torch.zeros((rows + 2 * bands.HALO, self.row_stride), dtype=torch.uint8)
-        self._band = E.Band(width, rows)
+        self._band = E.Band(width, rows, ucap, force_global)
         self.seam_bytes = self._band.seam_words * 4
         self._map2 = None
         self._all = None
@@ -51,7 +51,7 @@ class EmuBandBackend:
         self._band.hysteresis(self._map2)
 
     def seam_record(self):
-        return torch.from_numpy(self._band.publish().view(np.uint8))
+        return torch.from_numpy(self._band.record.view(np.uint8))
 
     def gather_buffer(self, world):
         if self._all is None or self._all.numel() != world * self.seam_bytes:
@@ -162,12 +162,12 @@ def test_cross_band_hysteresis_one_exchange():
     assert exchanges == 1
 
 
-def _local(t, world):
+def _local(t, world, ucap=0, force_global=False):
     h, w = t.shape
     bes = []
     for r in range(world):
         y0, rows = bands.band_rows(h, world, r)
-        bes.append(EmuBandBackend(w, rows, y0, h, thresh_override=t[y0:y0 + rows]))
+        bes.append(EmuBandBackend(w, rows, y0, h, thresh_override=t[y0:y0 + rows], ucap=ucap, force_global=force_global))
     n = bands.run_local(bes)
     return np.concatenate([b.edges() for b in bes]), n
 
@@ -179,9 +179,10 @@ def test_run_local_single_process_bands():
     assert np.array_equal(got, O.hysteresis(t)) and n == 1
 
 
+@pytest.mark.parametrize("force_global", [False, True], ids=["smem", "gmem"])
 @pytest.mark.parametrize("world", [2, 4, 7])
 @pytest.mark.parametrize("seed", [0, 1, 2])
-def test_seam_solve_random_maps(world, seed):
+def test_seam_solve_random_maps(world, seed, force_global):
     """Random weak clutter with few strong pixels: many components thread through several bands, some reach an edge
     only through a chain of other bands' unresolved components.  Widths around the 32-bit word boundaries."""
     rng = np.random.default_rng(seed)
@@ -190,7 +191,16 @@ def test_seam_solve_random_maps(world, seed):
     r = rng.random((h, w))
     t = np.where(r < 0.42, 128, 0).astype(np.uint8)
     t[rng.random((h, w)) < 0.004] = 255
-    got, _ = _local(t, world)
+    got, _ = _local(t, world, force_global=force_global)
+    assert np.array_equal(got, O.hysteresis(t))
+
+
+def test_unresolved_word_list_overflow_falls_back_to_full_pass():
+    """A list capacity of 3 words: the pass after the solve must visit the whole band instead."""
+    rng = np.random.default_rng(9)
+    t = np.where(rng.random((40, 200)) < 0.4, 128, 0).astype(np.uint8)
+    t[rng.random(t.shape) < 0.003] = 255
+    got, _ = _local(t, 3, ucap=3)
     assert np.array_equal(got, O.hysteresis(t))
 
 

@@ -56,7 +56,7 @@ def test_local_bands_equal_unsharded(kind, w, h, nb):
         assert abs(T.seam_excess_vs_unsharded(got, want, T.cv_canny(img), nb)) <= 0.1
 
 
-def _thresh_bands(t, nb, p2p):
+def _thresh_bands(t, nb, p2p, force_global=False):
     """Hysteresis-only band run on a given thresholded map (u8 0/128/255) split into nb bands on cuda:0."""
     h, w = t.shape
     bes = []
@@ -64,6 +64,8 @@ def _thresh_bands(t, nb, p2p):
         y0, rows = bands.band_rows(h, nb, r)
         b = bands.CudaBandBackend(w, rows, y0, h, device=0)
         b.load_thresh(t[y0:y0 + rows])
+        if force_global:
+            _lib.check(_lib.lib.b2c_set_option(b._h, b"seam_force_global", 1), b._h, "set_option")
         bes.append(b)
     if p2p:
         bands.open_local(bes)
@@ -87,6 +89,7 @@ def test_seam_solve_snake_and_clutter_on_device(p2p):
     t = np.where(rng.random((203, 1500)) < 0.4, 128, 0).astype(np.uint8)
     t[rng.random(t.shape) < 0.001] = 255
     assert np.array_equal(_thresh_bands(t, 8, p2p), O.hysteresis(t))
+    assert np.array_equal(_thresh_bands(t, 8, p2p, force_global=True), O.hysteresis(t))   # global-memory hash / forest
 
 
 def test_giga_bands_hash_equals_golden():

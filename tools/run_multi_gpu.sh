@@ -17,12 +17,13 @@ for g in ${GS:-1 2 4 8}; do
     esac
   done
 done
+if [ $N -gt 1 ]; then python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 tools/band_phases.py 2>&1 | grep "rank"; fi
 python - <<'PY'
 import json, glob
 for f in sorted(glob.glob("gpurun_out/scale_*_n*.json")):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
-        print(f.split("/")[-1], "n", d["n_gpus"], "value %.0f Mpx/s  ms/step %.3f  e2e %.0f" % (d["value"], d["ms_per_step"], d["e2e"]["value"]), d["config"].get("global_hysteresis_rounds", ""))
+        print(f.split("/")[-1], "n", d["n_gpus"], "value %.0f Mpx/s  ms/step %.3f  e2e %.0f" % (d["value"], d["ms_per_step"], d["e2e"]["value"]), (d.get("giga") or {}).get("phase_us_rank0", ""), (d.get("giga") or {}).get("equals_oracle_golden", ""))
     except Exception as e:
         print(f, "unreadable", e)
 PY
