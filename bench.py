@@ -103,7 +103,7 @@ class ClockSampler:
             time.sleep(0.002)
 
     def start(self):
-        if self.nv:
+        if self.nv and os.environ.get("B2C_NO_SAMPLER", "0") != "1":
             self._t = threading.Thread(target=self._loop, daemon=True)
             self._t.start()
 

@@ -127,8 +127,8 @@ class CudaBandBackend:
         self.p2p = True
 
     def stencil_p2p(self, phase=0):
-        """Halo exchange over peer memory hidden behind the stencil of the rows that need no halo.
-        phase: 0 = all (one band per process), 1 = push + interior rows, 2 = wait + seam strips (see run_local)."""
+        """Halo exchange over peer memory hidden behind the stencil: only the CTAs next to a seam wait for the rows.
+        phase: 0 = all (one band per process), 1 = push, 2 = stencil (see run_local)."""
         _lib.check(_lib.lib.b2c_band_p2p_stencil(self._h, self._stream(), phase), self._h, "b2c_band_p2p_stencil")
 
     def seam_p2p(self):
@@ -139,7 +139,7 @@ class CudaBandBackend:
         names = ("tile_border", "publish_push", "resolve", "gap", "wait_solve", "list_pass")
         d = {n: _lib.lib.b2c_get_info(self._h, b"seam_phase_us%d" % k) for k, n in enumerate(names)}
         if self.p2p:
-            d.update({n: _lib.lib.b2c_get_info(self._h, b"band_stencil_us%d" % k) for k, n in enumerate(("push_interior", "halo_wait", "strips"))})
+            d.update({n: _lib.lib.b2c_get_info(self._h, b"band_stencil_us%d" % k) for k, n in enumerate(("halo_push", "gap", "stencil"))})
         return d
 
     def set_phase_timing(self, on):

@@ -85,7 +85,8 @@ struct b2c_ctx {
   uint8_t *h_in[NSLOT] = { nullptr, nullptr };
   uint8_t *h_out[NSLOT] = { nullptr, nullptr };
   size_t h_in_bytes = 0, h_out_bytes = 0;
-  cudaStream_t s_main = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  cudaStream_t s_main = nullptr, s_h2d = nullptr, s_d2h = nullptr, s_side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_in[NSLOT] = {}, ev_k[NSLOT] = {}, ev_out[NSLOT] = {};
   cudaEvent_t ev_h[4] = {};   // hysteresis phase marks (only with the hyst_phase_timing option)
   bool hyst_phase_timing = false;
@@ -101,7 +102,7 @@ struct b2c_ctx {
   int *d_seam_ctl = nullptr, *h_seam_ctl = nullptr;   // [0] promoted flag, [2] peer time-out, [3] runs promoted, [4] length of ulist
   uint2 *d_ulist = nullptr;                // plane words that keep unresolved weak pixels after the band-local resolve
   int ucap = 0;
-  cudaEvent_t ev_b[4] = {};                // phase marks of b2c_band_p2p_stencil: start, after push + interior rows, after the wait, end
+  cudaEvent_t ev_b[4] = {};                // phase marks of b2c_band_p2p_stencil: start, after the push, before the stencil, end
   cudaEvent_t ev_s[7] = {};                // phase marks of the band hysteresis / seam pass (hyst_phase_timing option)
   int seam_run = 0;
   bool seam_force_global = false;          // test option: global-memory hash / forest in the seam kernels
@@ -195,6 +196,11 @@ int alloc_common(b2c_ctx *c)
   CK(c, cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking));
   CK(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
   CK(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+  if (c->band) {   // side stream of the peer-to-peer pushes
+    CK(c, cudaStreamCreateWithFlags(&c->s_side, cudaStreamNonBlocking));
+    CK(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CK(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  }
   for (int i = 0; i < NSLOT; ++i) {
     CK(c, cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
     CK(c, cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
@@ -421,6 +427,7 @@ void b2c_destroy(b2c_handle c)
   if (c->s_main) cudaStreamSynchronize(c->s_main);
   if (c->s_h2d) cudaStreamSynchronize(c->s_h2d);
   if (c->s_d2h) cudaStreamSynchronize(c->s_d2h);
+  if (c->s_side) cudaStreamSynchronize(c->s_side);
   cudaFree(c->d_in);
   cudaFree(c->d_map2);
   cudaFree(c->d_S_base);
@@ -473,6 +480,9 @@ void b2c_destroy(b2c_handle c)
   if (c->s_main) cudaStreamDestroy(c->s_main);
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
   if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+  if (c->s_side) cudaStreamDestroy(c->s_side);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   (void)cudaGetLastError();
   delete c;
 }
@@ -886,7 +896,7 @@ int b2c_load_thresh(b2c_handle c, const uint8_t *host_thresh, size_t row_stride)
 
 // ---- row-band mode --------------------------------------------------------------------------------
 // Order of one band step (stream order; [p2p] = only with peer wiring):
-//   [halo push] stencil interior rows [halo wait] stencil edge rows | k_uf_tile, k_uf_border, k_seam_publish [+ push],
+//   [halo push] stencil (its CTAs next to a seam wait for the halo rows) | k_uf_tile, k_uf_border, k_seam_publish [+ push],
 //   k_uf_resolve<LIST> | k_seam_solve [waits for the peers' records first], k_uf_resolve_list
 // The halo rows travel while the interior rows are computed, the seam records while the band resolves.
 namespace
@@ -943,8 +953,7 @@ int launch_stencil_rows(b2c_ctx *c, const uint8_t *band_row0, size_t row_stride,
   p.y0 = c->band_y0 + r0;
   p.pl_S += (long long)r0 * p.pl_pitch16;
   p.pl_C += (long long)r0 * p.pl_pitch16;
-  // (a strip of a few rows: 256-thread tiles finish sooner than one-warp CTAs marching 12 rows each)
-  if (c->stencil_impl == 0 && nrows > 8 && b2c::march_supported(p)) {
+  if (c->stencil_impl == 0 && b2c::march_supported(p)) {
     cudaError_t e = b2c::march_launch(p, c->sm_count, c->march_ctas_per_sm, r0 == 0 && nrows == c->rows_alloc ? c->march_rb : 0, st, c->march_extra_smem);
     if (e != cudaSuccess) return set_err(c, e, "k_stencil_march launch");
   } else {
@@ -991,18 +1000,23 @@ int b2c_band_hysteresis(b2c_handle c, void *stream)
   const int world = c->p2p_world, rank = c->p2p_rank, par = c->seam_run & 1;
   const bool p2p = world >= 2 && c->d_mailbox;
   uint32_t *rec = p2p ? own_mail(c) + b2c::bp_seam_slot(c->wpr, par, rank) : c->d_seam_rec;
-  b2c::B2cSeamPeers q;
-  memset(&q, 0, sizeof(q));
-  if (p2p) {   // the publishing CTA also stores the record into every rank's mailbox
+  b2c::k_seam_publish<<<1, b2c::SEAM_THREADS, b2c::seam_publish_smem(c->wpr), st>>>(b, rec, c->seam_run);
+  c->launches += 3;
+  if (p2p) {   // the record travels to every rank's mailbox on the side stream while this stream resolves the band
+    b2c::B2cSeamPeers q;
+    memset(&q, 0, sizeof(q));
     for (int k = 0; k < world; ++k) {
       q.slot[k] = (uint32_t *)c->peer_mail[k] + b2c::bp_seam_slot(c->wpr, par, rank);
       q.flag[k] = (uint32_t *)c->peer_mail[k] + b2c::bp_seam_flag(c->wpr, par, rank);
     }
     q.world = world;
     q.rank = rank;
+    CK(c, cudaEventRecord(c->ev_fork, st));
+    CK(c, cudaStreamWaitEvent(c->s_side, c->ev_fork, 0));
+    b2c::k_seam_push<<<1, b2c::SEAM_THREADS, 0, c->s_side>>>(q, c->wpr, c->seam_run);
+    CK(c, cudaEventRecord(c->ev_join, c->s_side));
+    c->launches++;
   }
-  b2c::k_seam_publish<<<1, b2c::SEAM_THREADS, b2c::seam_publish_smem(c->wpr), st>>>(b, rec, c->seam_run, q);
-  c->launches += 3;
   if (pt) cudaEventRecord(c->ev_s[2], st);
   // resolve + expansion; the words that stay unresolved go to the list of the seam pass
   const int tx = c->wpr >= 256 ? 256 : c->wpr > 32 ? 64 : 32, ty = 256 / tx;
@@ -1074,6 +1088,7 @@ int b2c_band_status(b2c_handle c, int *promoted_runs, int *error)
   DevGuard g(c->dev);
   CK(c, cudaDeviceSynchronize());   // the band's work may be on any stream
   CK(c, cudaMemcpy(c->h_seam_ctl, c->d_seam_ctl, 8 * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(c, cudaMemset(c->d_seam_ctl + 2, 0, sizeof(int)));   // a time-out is reported once
   if (promoted_runs) *promoted_runs = c->h_seam_ctl[3];
   if (error) *error = c->h_seam_ctl[2];
   return B2C_OK;
@@ -1202,11 +1217,12 @@ void fill_p2p(b2c_ctx *c, b2c::B2cBandP2P &q)
 }// namespace
 
 // Stencil of the band in the handle's own input buffer (b2c_band_input) with the halo exchange over peer memory hidden
-// behind it: my first / last 4 rows are stored into the neighbours' buffers, the rows that need no halo (all but the
-// first / last 4 of a band with a neighbour on that side) are computed, and only the 4-row strips next to a seam wait for
-// the neighbours' rows.  phase: B2C_P2P_ALL, or B2C_P2P_PUSH (push + interior rows) then B2C_P2P_WAIT (wait + strips): a
-// single-process driver of several bands issues ALL pushes before the first wait -- a device-side wait must never be
-// queued ahead of the store it waits for.
+// behind it: my first / last 4 rows are stored into the neighbours' buffers, then ONE stencil launch over the whole band
+// whose CTAs next to a seam wait -- on the device, when they get there -- for the neighbour's arrival counter (the
+// marching kernel; geometries it does not take wait in a kernel of their own before the launch).
+// phase: B2C_P2P_ALL, or B2C_P2P_PUSH (the stores) then B2C_P2P_WAIT (the stencil): a single-process driver of several
+// bands issues ALL pushes before the first stencil -- a device-side wait must never be queued ahead of the store it
+// waits for.
 int b2c_band_p2p_stencil(b2c_handle c, void *stream, int phase)
 {
   if (!c || !c->band || c->p2p_world < 2 || !c->d_band_in || phase < B2C_P2P_ALL || phase > B2C_P2P_WAIT) return B2C_ERR_INVALID;
@@ -1216,32 +1232,48 @@ int b2c_band_p2p_stencil(b2c_handle c, void *stream, int phase)
   fill_p2p(c, q);
   const size_t stride = (size_t)q.in_stride;
   const uint8_t *row0 = c->d_band_in + 4 * stride;
-  const int rows = c->rows_alloc, cpr = (c->w * 3 + 15) / 16, nblocks = (4 * cpr + 255) / 256;
+  const int cpr = (c->w * 3 + 15) / 16, nblocks = (4 * cpr + 255) / 256;
   const bool up = c->p2p_rank > 0, dn = c->p2p_rank < c->p2p_world - 1;
-  // rows [i0, i1) need no halo row; a band of fewer than 8 rows between two seams has none
-  const int i0 = up ? 4 : 0, i1 = std::max(i0, dn ? rows - 4 : rows);
-  int rc = B2C_OK;
   const bool pt = c->hyst_phase_timing;
   if (phase != B2C_P2P_WAIT) {
     if (pt) cudaEventRecord(c->ev_b[0], st);
     c->p2p_run += 1;
-    CK(c, cudaMemsetAsync(c->d_seam_ctl + 2, 0, sizeof(int), st));   // a time-out of an earlier run is not sticky
-    b2c::k_band_push_halo<<<dim3(nblocks, 2), 256, 0, st>>>(q);
+    // on the side stream, behind whatever filled the input buffer on `stream`: the stencil does not wait for the stores
+    CK(c, cudaEventRecord(c->ev_fork, st));
+    CK(c, cudaStreamWaitEvent(c->s_side, c->ev_fork, 0));
+    b2c::k_band_push_halo<<<dim3(nblocks, 2), 256, 0, c->s_side>>>(q);
+    CK(c, cudaEventRecord(c->ev_join, c->s_side));
     c->launches++;
-    rc = launch_stencil_rows(c, row0, stride, i0, i1 - i0, st);
-    if (rc != B2C_OK) return rc;
     if (pt) cudaEventRecord(c->ev_b[1], st);
   }
   if (phase != B2C_P2P_PUSH) {
-    b2c::k_band_wait_halo<<<1, 1, 0, st>>>(q, c->p2p_run, nblocks);
-    c->launches++;
-    if (pt) cudaEventRecord(c->ev_b[2], st);
-    if (up) rc = launch_stencil_rows(c, row0, stride, 0, std::min(i0, rows), st);
-    if (rc == B2C_OK && dn && i1 < rows) rc = launch_stencil_rows(c, row0, stride, std::max(i1, i0), rows - std::max(i1, i0), st);
+    B2cStencilParams p;
+    fill_stencil_params(c, p, row0, stride, 0, 1);
+    if (c->stencil_impl == 0 && b2c::march_supported(p)) {
+      const uint32_t *mine = own_mail(c);
+      p.halo_cnt_up = up ? mine + b2c::bp_halo_flag(c->wpr, 0) : nullptr;   // rows from above
+      p.halo_cnt_dn = dn ? mine + b2c::bp_halo_flag(c->wpr, 1) : nullptr;   // rows from below
+      p.halo_need = c->p2p_run * nblocks;
+      p.halo_err = c->d_seam_ctl + 2;
+      if (pt) cudaEventRecord(c->ev_b[2], st);
+      cudaError_t e = b2c::march_launch(p, c->sm_count, c->march_ctas_per_sm, c->march_rb, st, c->march_extra_smem);
+      if (e != cudaSuccess) return set_err(c, e, "k_stencil_march launch");
+      c->launches++;
+      c->map2_valid = false;
+      c->edges_valid = false;
+      c->have_frame = true;
+    } else {
+      b2c::k_band_wait_halo<<<1, 1, 0, st>>>(q, c->p2p_run, nblocks);
+      c->launches++;
+      if (pt) cudaEventRecord(c->ev_b[2], st);
+      int rc = launch_stencil_rows(c, row0, stride, 0, c->rows_alloc, st);
+      if (rc != B2C_OK) return rc;
+    }
+    CK(c, cudaStreamWaitEvent(st, c->ev_join, 0));   // later work on `stream` (a new image in the input buffer) follows my stores
     if (pt) cudaEventRecord(c->ev_b[3], st);
   }
   CK(c, cudaGetLastError());
-  return rc;
+  return B2C_OK;
 }
 
 // cross-band hysteresis over peer memory, after b2c_band_hysteresis (which published and pushed my record): wait for all
@@ -1253,6 +1285,7 @@ int b2c_band_p2p_seam(b2c_handle c, void *stream)
   cudaStream_t st = stream ? (cudaStream_t)stream : c->s_main;
   const int world = c->p2p_world, rank = c->p2p_rank, par = c->seam_run & 1;
   uint32_t *mine = own_mail(c);
+  CK(c, cudaStreamWaitEvent(st, c->ev_join, 0));   // my own push (long finished: the band resolved meanwhile)
   if (c->hyst_phase_timing) cudaEventRecord(c->ev_s[4], st);
   const uint32_t *recs[b2c::SEAM_MAXW];
   for (int r = 0; r < world; ++r) recs[r] = mine + b2c::bp_seam_slot(c->wpr, par, r);
@@ -1323,7 +1356,7 @@ int b2c_set_option(b2c_handle c, const char *name, int value)
 int b2c_get_info(b2c_handle c, const char *name)
 {
   if (!c || !name) return B2C_ERR_INVALID;
-  if (!strncmp(name, "band_stencil_us", 15)) {   // b2c_band_p2p_stencil with "hyst_phase_timing": push + interior rows, wait, seam strips (us)
+  if (!strncmp(name, "band_stencil_us", 15)) {   // b2c_band_p2p_stencil with "hyst_phase_timing": halo push, gap, stencil incl. its waits (us)
     const int k = name[15] - '0';
     if (k < 0 || k > 2 || !c->ev_b[0]) return B2C_ERR_INVALID;
     float ms = 0;

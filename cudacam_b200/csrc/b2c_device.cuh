@@ -60,6 +60,12 @@ struct B2cStencilParams {
   uint8_t *mono, *blur, *nms, *thresh;
   float *grad;
   int pitch8, pitchf;        // in elements
+  // row bands over peer memory (marching kernel only; null = off): the neighbours store the 4 halo rows above / below
+  // the band while this launch already runs; the CTAs that read them first wait until the arrival counter (system
+  // scope) reaches halo_need.  halo_err: set to 1 after a 2 s time-out.
+  const uint32_t *halo_cnt_up, *halo_cnt_dn;
+  int halo_need;
+  int *halo_err;
 };
 
 struct B2cHystParams {

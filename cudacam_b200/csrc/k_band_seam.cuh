@@ -166,8 +166,8 @@ __device__ __forceinline__ void seam_union(int *P, int a, int b)
   }
 }
 
-// ---- publish (+ push): one CTA ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SEAM_THREADS) k_seam_publish(const B2cSeamBand b, uint32_t *rec, const int run_id, const B2cSeamPeers q)
+// ---- publish: one CTA ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEAM_THREADS) k_seam_publish(const B2cSeamBand b, uint32_t *rec, const int run_id)
 {
   B2C_DYN_SMEM(smem);
   int *cnt = reinterpret_cast<int *>(smem);               // [2 * wpr] run starts per word, then their exclusive prefix
@@ -246,22 +246,25 @@ __global__ void __launch_bounds__(SEAM_THREADS) k_seam_publish(const B2cSeamBand
     rec[4] = (uint32_t)cap;
     b.ctl[1] = run_id;
   }
-#ifndef B2C_EMU
-  // 4. peer wiring: the used part of the record -> every other rank's mailbox, then the flags (release, system scope)
-  if (q.world > 1) {
-    __threadfence();
-    __syncthreads();
-    const int words = SEAM_HDR + 6 * wpr + total;
-    for (int i = tid; i < words * q.world; i += nt) {
-      const int peer = i / words, k = i - peer * words;
-      if (peer != q.rank) q.slot[peer][k] = __ldcg(rec + k);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < q.world) seam_store_release_sys(q.flag[tid], (uint32_t)run_id);
-  }
-#endif
 }
+
+#ifndef B2C_EMU
+// peer wiring: the used part of my record (in my own mailbox) -> every other rank's mailbox, then the arrival flags
+// (release, system scope; my own flag too).  One CTA, on a side stream: the band resolves meanwhile.
+__global__ void __launch_bounds__(SEAM_THREADS) k_seam_push(const B2cSeamPeers q, const int wpr, const int run_id)
+{
+  const uint32_t *rec = q.slot[q.rank];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int words = SEAM_HDR + 6 * wpr + (int)(__ldcg(rec + 1) + __ldcg(rec + 2));
+  for (int i = tid; i < words * q.world; i += nt) {
+    const int peer = i / words, k = i - peer * words;
+    if (peer != q.rank) q.slot[peer][k] = __ldcg(rec + k);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < q.world) seam_store_release_sys(q.flag[tid], (uint32_t)run_id);
+}
+#endif
 
 // ---- solve: one CTA ---------------------------------------------------------------------------------------------
 // run ordinal (within its band: first-row runs, then last-row runs) of the run that contains bit `bit` of word w of a

@@ -687,7 +687,32 @@ __device__ __forceinline__ void m_c_block(const B2cStencilParams &p, const March
   }
 }
 
-template <int CH>
+// Row bands over peer memory: spin until the neighbour's halo rows have landed, 2 s time-out.  Every lane polls the same
+// word and the exit condition goes through a shuffle: a loop the compiler can prove warp-uniform (a divergent one in
+// front of the marching code would make it compile every later shuffle and vote with a divergence fallback).
+__device__ __forceinline__ void m_halo_wait(const uint32_t *cnt, const int need, int *err)
+{
+#ifndef B2C_EMU
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+  for (;;) {
+    uint32_t v;
+    unsigned long long t;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    const int st = (int)v >= need ? 1 : (t - t0 > 2000000000ull ? 2 : 0);
+    const int s0 = __shfl_sync(B2C_FULL, st, 0);
+    if (s0) {
+      if (s0 == 2) *err = 1;
+      break;
+    }
+  }
+  asm volatile("fence.acq_rel.sys;" ::: "memory");
+#endif
+}
+
+// HALO: row bands over peer memory (the plain instance carries none of it)
+template <int CH, bool HALO = false>
 __global__ void __launch_bounds__(MARCH_THREADS, MARCH_CTAS_PER_SM) k_stencil_march(const B2cStencilParams p, const int rb)
 {
   B2C_DYN_SMEM(smem);
@@ -717,6 +742,13 @@ __global__ void __launch_bounds__(MARCH_THREADS, MARCH_CTAS_PER_SM) k_stencil_ma
   // that IS the reference's per-stage zero padding left and right of the image (cannyEdgeD.cu:142-149, 222-229).
   for (int i = threadIdx.x; i < MARCH_SMEM / 16; i += MARCH_THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
+  // halo rows of a row band that arrive while the launch runs: only the CTAs of the first / last band of rows read them,
+  // and wait here (the neighbour's stores were issued before its own stencil: a few microseconds at most, while all other
+  // CTAs of the launch are already at work)
+  if (HALO) {
+    if (p.halo_cnt_up != nullptr && blockIdx.y == 0) m_halo_wait(p.halo_cnt_up, p.halo_need, p.halo_err);
+    if (p.halo_cnt_dn != nullptr && blockIdx.y == gridDim.y - 1) m_halo_wait(p.halo_cnt_dn, p.halo_need, p.halo_err);
+  }
   if (MARCH_DUO) {
 #if B2C_X & 12
     // profiling builds: one of the two warps only keeps the hand-over protocol alive
@@ -781,6 +813,8 @@ inline cudaError_t march_configure(int *ctas_per_sm)
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_stencil_march<3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_stencil_march<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_stencil_march<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_stencil_march<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_stencil_march<3, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   if (e == cudaSuccess && ctas_per_sm) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_stencil_march<3>, MARCH_THREADS, MARCH_SMEM);
   return e;
 }
@@ -819,7 +853,8 @@ inline cudaError_t march_launch(const B2cStencilParams &p, int sm_count, int cta
   const int smem_bytes = MARCH_SMEM + extra_smem;   // (extra_smem: profiling knob that lowers the number of resident CTAs)
   const int rb = rb_override > 0 ? rb_override : march_band_rows(p.w, p.h, p.nframes, sm_count, ctas_per_sm);
   dim3 grid((p.w + MT_X - 1) / MT_X, (p.h + rb - 1) / rb, p.nframes);
-  if (p.channels == 1) k_stencil_march<1><<<grid, MARCH_THREADS, smem_bytes, st>>>(p, rb);
+  if (p.halo_cnt_up || p.halo_cnt_dn) k_stencil_march<3, true><<<grid, MARCH_THREADS, smem_bytes, st>>>(p, rb);   // (row bands are BGR8)
+  else if (p.channels == 1) k_stencil_march<1><<<grid, MARCH_THREADS, smem_bytes, st>>>(p, rb);
   else if (p.channels == 4) k_stencil_march<4><<<grid, MARCH_THREADS, smem_bytes, st>>>(p, rb);
   else k_stencil_march<3><<<grid, MARCH_THREADS, smem_bytes, st>>>(p, rb);
   return cudaGetLastError();

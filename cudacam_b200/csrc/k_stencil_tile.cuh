@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(TILE_THREADS) k_stencil_tile(const B2cStencilP
     const int r = i / MW, c = i - r * MW;
     const int y = y0t + r - 4, x = x0 + c - 4, yg = y + p.y0;
     unsigned v = 0;
-    if (x >= 0 && x < p.w && yg >= 0 && yg < p.h_glob) {
+    // (rows past the 4 halo rows below the band / frame feed no stored pixel and may lie outside the caller's buffer)
+    if (x >= 0 && x < p.w && yg >= 0 && yg < p.h_glob && y < p.h + 4) {
       const uint8_t *q = src + (long long)y * p.row_stride + p.channels * x;
       v = p.channels == 1 ? q[0] : (q[0] * 7u + q[1] * 38u + q[2] * 19u) >> 6;   // BGR8 / BGRA8 (alpha ignored) / GRAY8
     }

@@ -157,14 +157,16 @@ B2C_API int b2c_band_status(b2c_handle h, int *promoted_runs, int *error);
  * instead of collectives, hidden behind the band's own work:
  * b2c_band_input: the band's input buffer owned by the handle (so that it can be shared): rows 0..3 = halo rows above
  *   the band, rows 4..4+band_rows-1 = the band, then 4 halo rows; rows are row_stride bytes apart;
- * b2c_band_p2p_stencil: stencil of the band in that buffer: my first / last 4 rows -> the neighbours' buffers, the rows
- *   that need no halo are computed meanwhile, only the 4-row strips at the seams wait for the neighbours' rows;
+ * b2c_band_p2p_stencil: stencil of the band in that buffer: my first / last 4 rows -> the neighbours' buffers, then one
+ *   stencil launch whose thread blocks next to a seam wait on the device for the neighbour's rows when they need them;
  * b2c_band_hysteresis (on a wired handle): also stores the seam record into every rank's mailbox before it resolves;
  * b2c_band_p2p_seam: waits for all records, solves, promotes (replaces the gather + b2c_band_seam_solve above).
  * phase: B2C_P2P_ALL for a rank that drives one band.  A process that drives SEVERAL bands (b2c_band_p2p_open_local)
- * gives every band its own stream and issues, band by band, b2c_band_p2p_stencil(PUSH), then (WAIT), then
+ * gives every band its own stream and issues, band by band, b2c_band_p2p_stencil(PUSH = the stores), then (WAIT = the
+ * stencil), then
  * b2c_band_hysteresis, then b2c_band_p2p_seam: the waits spin on the device and must never be queued ahead of the
- * stores they wait for.  Every wait has a 2 s time-out (b2c_band_status reports it, the next run clears it). */
+ * stores they wait for.  Every wait has a 2 s time-out (b2c_band_status reports it once).  The stores run on a side stream
+ * of the handle; work enqueued on `stream` after these calls is ordered behind them. */
 enum { B2C_P2P_ALL = 0, B2C_P2P_PUSH = 1, B2C_P2P_WAIT = 2 };
 B2C_API int b2c_band_input(b2c_handle h, void **dev_ptr, size_t *row_stride);
 B2C_API int b2c_band_p2p_export(b2c_handle h, void *blob_144);

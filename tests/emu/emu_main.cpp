@@ -215,9 +215,7 @@ __attribute__((visibility("default"))) void emu_band_hysteresis(void *h, const u
   const b2c::B2cSeamBand s = emu_seam_band(b);
   const int run = ++b->run;
   uint32_t *rec = b->rec.data();
-  b2c::B2cSeamPeers q;
-  memset(&q, 0, sizeof(q));
-  emu::launch(dim3(1), dim3(EMU_SEAM_THREADS), b2c::seam_publish_smem(P.wpr), false, [=] { b2c::k_seam_publish(s, rec, run, q); });
+  emu::launch(dim3(1), dim3(EMU_SEAM_THREADS), b2c::seam_publish_smem(P.wpr), false, [=] { b2c::k_seam_publish(s, rec, run); });
   const int tx = 32, ty = 4;
   const dim3 gr((P.wpr + tx - 1) / tx, (P.h + 2 * ty - 1) / (2 * ty), 1), br(tx, ty);
   uint2 *ul = b->ulist.data();
