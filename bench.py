@@ -447,6 +447,9 @@ def run_ours(args, wl):
     from cudacam_b200 import _lib, synth
     lib = _lib.lib
     world, rank, local = env.world, env.rank, env.local
+    # one process per GPU: keep this rank's threads and its pinned rings on the NUMA node of its GPU (-1: platform silent)
+    # (only with several ranks: the N=1 run also times the CPU baseline on ALL host cores)
+    numa_node = lib.b2c_bind_host_to_device(local) if world > 1 else None
     w, h, n = wl["w"], wl["h"], wl["n"]
     warmup = max(args.warmup, 3)
     reps = 1
@@ -574,7 +577,7 @@ def run_ours(args, wl):
                          "traffic": traffic, "peak_source": which, "algorithmic_bytes_per_launch": px_per_chunk * STENCIL_BYTES_PER_PX,
                          "kernel_ms": k_ms, "hysteresis_ms": statistics.mean(hyst_ms), "stencil_share_of_step": sum(stencil_ms) / (sum(stencil_ms) + sum(hyst_ms))},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": px_per_step * 3, "d2h_bytes_per_step": px_per_step, "steps": e2e_steps,
-                    "api": "b2c_run_batch_host (pinned host frames in, host u8 edge maps out)",
+                    "api": "b2c_run_batch_host (pinned host frames in, host u8 edge maps out; 8 slots of 8 frames on 3 streams)", "numa_node_rank0": numa_node,
                     "h2d_gbs_per_gpu": e2e_value * 3 / 1e3 / world, "packed_bits_value": e2e_bits, "packed_bits_d2h_bytes_per_step": n * h * wpr * 4 * reps,
                     "pcie_ceiling_rank0": ceiling},
             "oracle_check": oracle_check,

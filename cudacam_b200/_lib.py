@@ -63,6 +63,7 @@ _SIGS = {
     "b2c_last_cuda_error": (C.c_char_p, [_vp]),
     "b2c_version": (C.c_char_p, []),
     "b2c_device_count": (_i, []),
+    "b2c_bind_host_to_device": (_i, [_i]),
     "b2c_launch_count": (C.c_longlong, [_vp]),
     "b2c_set_option": (_i, [_vp, C.c_char_p, _i]),
     "b2c_get_info": (_i, [_vp, C.c_char_p]),

@@ -12,9 +12,12 @@
 // plus what the reference does not have: device-resident batches, a pinned double-buffered host
 // pipeline, and row-band mode for one image split over several GPUs.
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -32,7 +35,8 @@
 
 namespace
 {
-constexpr int NSLOT = 2;   // ping-pong halves of the batch buffers in the host pipeline
+constexpr int NSLOT = 8;        // slots of the host pipeline: the batch buffers (input, planes, forest, edge maps) are cut into up to 8 slots
+constexpr int SLOT_FRAMES = 8;  // of at most 8 frames, so that only one small upload and one small download stay exposed
 
 struct Ev {
   cudaEvent_t e = nullptr;
@@ -77,13 +81,14 @@ struct b2c_ctx {
 
   // last input (for on-demand stage buffers)
   const uint8_t *last_in = nullptr;
+  int acc_frame = 0;   // batch slot (first frame) the accessors of "frame 0 of the last run" read
   size_t last_row_stride = 0;
   bool have_frame = false, stages_valid = false, edges_valid = false, map2_valid = false;
   int last_stage = -1;
 
   // host pipeline
-  uint8_t *h_in[NSLOT] = { nullptr, nullptr };
-  uint8_t *h_out[NSLOT] = { nullptr, nullptr };
+  uint8_t *h_in[NSLOT] = {};
+  uint8_t *h_out[NSLOT] = {};
   size_t h_in_bytes = 0, h_out_bytes = 0;
   cudaStream_t s_main = nullptr, s_h2d = nullptr, s_d2h = nullptr, s_side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -215,7 +220,8 @@ int alloc_common(b2c_ctx *c)
   return B2C_OK;
 }
 
-void fill_stencil_params(b2c_ctx *c, B2cStencilParams &p, const uint8_t *bgr, size_t row_stride, size_t frame_stride, int n)
+// frame0: first frame slot of the handle's batch buffers (planes, forest) this launch works in
+void fill_stencil_params(b2c_ctx *c, B2cStencilParams &p, const uint8_t *bgr, size_t row_stride, size_t frame_stride, int n, int frame0 = 0)
 {
   memset(&p, 0, sizeof(p));
   p.bgr = bgr;
@@ -228,8 +234,8 @@ void fill_stencil_params(b2c_ctx *c, B2cStencilParams &p, const uint8_t *bgr, si
   p.h_glob = c->band ? c->h_glob : c->h;
   p.nframes = n;
   p.channels = c->ch;
-  p.pl_S = reinterpret_cast<uint16_t *>(S0(c));
-  p.pl_C = reinterpret_cast<uint16_t *>(C0(c));
+  p.pl_S = reinterpret_cast<uint16_t *>(S0(c) + (long long)frame0 * plane_frame_stride(c));
+  p.pl_C = reinterpret_cast<uint16_t *>(C0(c) + (long long)frame0 * plane_frame_stride(c));
   p.pl_pitch16 = c->plane_pitch * 2;
   p.pl_frame_stride16 = plane_frame_stride(c) * 2;
   p.lo = c->lo;
@@ -241,10 +247,11 @@ void fill_stencil_params(b2c_ctx *c, B2cStencilParams &p, const uint8_t *bgr, si
 }
 
 // Fused stencil: BGR8 -> 2-bit map for n frames.
-int launch_stencil(b2c_ctx *c, const uint8_t *bgr, size_t row_stride, size_t frame_stride, int n, cudaStream_t st)
+int launch_stencil(b2c_ctx *c, const uint8_t *bgr, size_t row_stride, size_t frame_stride, int n, cudaStream_t st, int frame0 = 0)
 {
   B2cStencilParams p;
-  fill_stencil_params(c, p, bgr, row_stride, frame_stride, n);
+  fill_stencil_params(c, p, bgr, row_stride, frame_stride, n, frame0);
+  c->acc_frame = frame0;
   if (c->stencil_impl == 0 && b2c::march_supported(p)) {
     cudaError_t e = b2c::march_launch(p, c->sm_count, c->march_ctas_per_sm, c->march_rb, st, c->march_extra_smem);
     if (e != cudaSuccess) return set_err(c, e, "k_stencil_march launch");
@@ -286,12 +293,13 @@ int launch_stencil_emit(b2c_ctx *c, const uint8_t *bgr, size_t row_stride, cudaS
   return B2C_OK;
 }
 
-void fill_hyst_params(b2c_ctx *c, B2cHystParams &p, int n, uint8_t *edges, size_t edges_pitch, size_t edges_frame_stride)
+void fill_hyst_params(b2c_ctx *c, B2cHystParams &p, int n, uint8_t *edges, size_t edges_pitch, size_t edges_frame_stride, int frame0 = 0)
 {
   memset(&p, 0, sizeof(p));
-  p.S = S0(c);
-  p.C = C0(c);
-  p.E = E0(c);
+  const long long po = (long long)frame0 * plane_frame_stride(c);
+  p.S = S0(c) + po;
+  p.C = C0(c) + po;
+  p.E = E0(c) + po;
   p.plane_pitch = c->plane_pitch;
   p.plane_frame_stride = plane_frame_stride(c);
   p.w = c->w;
@@ -301,30 +309,32 @@ void fill_hyst_params(b2c_ctx *c, B2cHystParams &p, int n, uint8_t *edges, size_
   p.edges_pitch = (long long)edges_pitch;
   p.edges_frame_stride = (long long)edges_frame_stride;
   p.flags = c->d_flags;
-  p.parent = c->d_parent;
   p.parent_frame_stride = (long long)c->rows_alloc * c->plane_pitch * 32;
+  p.parent = c->d_parent + frame0 * p.parent_frame_stride;
   p.spread = c->uf_spread;
 }
 
 // Union-find hysteresis of n frames from the planes the stencil wrote: three ordinary launches (tile, border,
 // resolve + expansion to the u8 map), no barrier inside, no host round trip between.  edges == null: bit plane E only.
-int launch_hysteresis(b2c_ctx *c, int n, uint8_t *edges, size_t edges_pitch, size_t edges_frame_stride, cudaStream_t st)
+int launch_hysteresis(b2c_ctx *c, int n, uint8_t *edges, size_t edges_pitch, size_t edges_frame_stride, cudaStream_t st, int frame0 = 0)
 {
   B2cHystParams p;
-  fill_hyst_params(c, p, n, edges, edges_pitch, edges_frame_stride);
+  fill_hyst_params(c, p, n, edges, edges_pitch, edges_frame_stride, frame0);
+  uint32_t *blist = c->d_blist + (size_t)frame0 * c->bcap;
+  int *bcount = c->d_bcount + frame0;
   const dim3 gt((c->wpr + b2c::UT_WORDS - 1) / b2c::UT_WORDS, (c->rows_alloc + b2c::UT_ROWS - 1) / b2c::UT_ROWS, n);
   const bool pt = c->hyst_phase_timing;
   const int T = b2c::UFK_THREADS;
   if (pt) cudaEventRecord(c->ev_h[0], st);
-  b2c::k_uf_tile<<<gt, b2c::UT_THREADS, b2c::UT_SMEM, st>>>(p, c->d_blist, c->d_bcount, c->bcap);
+  b2c::k_uf_tile<<<gt, b2c::UT_THREADS, b2c::UT_SMEM, st>>>(p, blist, bcount, c->bcap);
   if (pt) cudaEventRecord(c->ev_h[1], st);
   // border list: typically ~12 % of bcap entries; 4 threads per entry, a quarter of the worst case in blocks, grid-stride for the rest
-  b2c::k_uf_border<<<dim3(std::max(1, (c->bcap + T - 1) / T), 1, n), T, 0, st>>>(p, c->d_blist, c->d_bcount, c->bcap);
+  b2c::k_uf_border<<<dim3(std::max(1, (c->bcap + T - 1) / T), 1, n), T, 0, st>>>(p, blist, bcount, c->bcap);
   if (pt) cudaEventRecord(c->ev_h[2], st);
   const int tx = c->wpr >= 256 ? 256 : c->wpr > 32 ? 64 : 32, ty = 256 / tx;   // 256 threads = tx words x ty rows
   const dim3 gr((c->wpr + tx - 1) / tx, (c->rows_alloc + 2 * ty - 1) / (2 * ty), n), br(tx, ty);   // a thread takes 2 rows
-  if (edges) b2c::k_uf_resolve<true><<<gr, br, 0, st>>>(p, c->d_bcount);
-  else b2c::k_uf_resolve<false><<<gr, br, 0, st>>>(p, c->d_bcount);
+  if (edges) b2c::k_uf_resolve<true><<<gr, br, 0, st>>>(p, bcount);
+  else b2c::k_uf_resolve<false><<<gr, br, 0, st>>>(p, bcount);
   if (pt) cudaEventRecord(c->ev_h[3], st);
   CK(c, cudaGetLastError());
   c->launches += 3;
@@ -634,8 +644,11 @@ int b2c_run_batch_host(b2c_handle c, const uint8_t *frames, size_t row_stride, i
   if (row_stride < (size_t)c->w * c->ch) return B2C_ERR_SIZE;
   DevGuard g(c->dev);
   const int w = c->w, h = c->h;
-  const int slot_frames = std::max(1, c->max_batch / NSLOT);
-  const int nslots = c->max_batch >= NSLOT ? NSLOT : 1;
+  // The batch buffers of the handle (input, planes, forest, edge maps: max_batch frames each) are cut into up to NSLOT
+  // slots of at most SLOT_FRAMES frames.  Chunk k lives in slot k % nslots: upload on s_h2d, kernels on s_main,
+  // download on s_d2h.  With 8-frame chunks only the first upload and the last download are not hidden.
+  const int slot_frames = std::max(1, std::min(SLOT_FRAMES, (c->max_batch + 1) / 2));
+  const int nslots = std::max(1, std::min(NSLOT, c->max_batch / slot_frames));
   const size_t in_frame_host = row_stride * h;
   const size_t out_row = packed_bits ? (size_t)c->wpr * 4 : (size_t)w;
   const size_t out_frame_host = out_row * h;
@@ -646,24 +659,25 @@ int b2c_run_batch_host(b2c_handle c, const uint8_t *frames, size_t row_stride, i
   const bool out_pinned = cudaPointerGetAttributes(&ao, edges_out) == cudaSuccess && ao.type == cudaMemoryTypeHost;
   (void)cudaGetLastError();
   if (!in_pinned && c->h_in_bytes < (size_t)slot_frames * in_frame_host) {
-    for (int s = 0; s < nslots; ++s) {
+    for (int s = 0; s < NSLOT; ++s) {
       if (c->h_in[s]) cudaFreeHost(c->h_in[s]);
       c->h_in[s] = nullptr;
-      CK(c, cudaMallocHost(&c->h_in[s], (size_t)slot_frames * in_frame_host));
     }
+    for (int s = 0; s < nslots; ++s) CK(c, cudaMallocHost(&c->h_in[s], (size_t)slot_frames * in_frame_host));
     c->h_in_bytes = (size_t)slot_frames * in_frame_host;
   }
   if (!out_pinned && c->h_out_bytes < (size_t)slot_frames * out_frame_host) {
-    for (int s = 0; s < nslots; ++s) {
+    for (int s = 0; s < NSLOT; ++s) {
       if (c->h_out[s]) cudaFreeHost(c->h_out[s]);
       c->h_out[s] = nullptr;
-      CK(c, cudaMallocHost(&c->h_out[s], (size_t)slot_frames * out_frame_host));
     }
+    for (int s = 0; s < nslots; ++s) CK(c, cudaMallocHost(&c->h_out[s], (size_t)slot_frames * out_frame_host));
     c->h_out_bytes = (size_t)slot_frames * out_frame_host;
   }
 
   const int nchunks = (n + slot_frames - 1) / slot_frames;
-  int pending_out[NSLOT] = { -1, -1 };   // chunk whose D2H into h_out[slot] still has to be copied out
+  int pending_out[NSLOT];   // chunk whose D2H into the slot's host buffer still has to be waited for / copied out
+  for (int &v : pending_out) v = -1;
   auto drain = [&](int slot) -> int {
     const int k = pending_out[slot];
     if (k < 0) return B2C_OK;
@@ -677,12 +691,12 @@ int b2c_run_batch_host(b2c_handle c, const uint8_t *frames, size_t row_stride, i
   };
 
   for (int k = 0; k < nchunks; ++k) {
-    const int slot = k % nslots;
+    const int slot = k % nslots, fr0 = slot * slot_frames;
     const int f0 = k * slot_frames, cnt = std::min(slot_frames, n - f0);
-    int rc = drain(slot);   // also guarantees the slot's device halves and pinned buffers are free
+    // the slot's previous chunk is completely through (its download has finished): every buffer of the slot is free
+    int rc = drain(slot);
     if (rc != B2C_OK) return rc;
-    if (k >= nslots) CK(c, cudaStreamWaitEvent(c->s_h2d, c->ev_k[slot], 0));   // input half still being read by chunk k-nslots
-    uint8_t *din = c->d_in + (size_t)slot * slot_frames * c->in_frame_stride;
+    uint8_t *din = c->d_in + (size_t)fr0 * c->in_frame_stride;
     const uint8_t *src = frames + (size_t)f0 * in_frame_host;
     if (!in_pinned) {
       memcpy(c->h_in[slot], src, (size_t)cnt * in_frame_host);
@@ -697,30 +711,24 @@ int b2c_run_batch_host(b2c_handle c, const uint8_t *frames, size_t row_stride, i
     CK(c, cudaEventRecord(c->ev_in[slot], c->s_h2d));
 
     CK(c, cudaStreamWaitEvent(c->s_main, c->ev_in[slot], 0));
-    if ((rc = launch_stencil(c, din, c->in_row_stride, c->in_frame_stride, cnt, c->s_main)) != B2C_OK) return rc;
-    uint8_t *dedges = c->d_edges + (size_t)slot * slot_frames * c->edges_frame_stride;
-    // all slots share the map / plane buffers: the compute stream serialises them
-    if ((rc = launch_hysteresis(c, cnt, packed_bits ? nullptr : dedges, c->edges_pitch, c->edges_frame_stride, c->s_main)) != B2C_OK) return rc;
+    if ((rc = launch_stencil(c, din, c->in_row_stride, c->in_frame_stride, cnt, c->s_main, fr0)) != B2C_OK) return rc;
+    uint8_t *dedges = c->d_edges + (size_t)fr0 * c->edges_frame_stride;
+    if ((rc = launch_hysteresis(c, cnt, packed_bits ? nullptr : dedges, c->edges_pitch, c->edges_frame_stride, c->s_main, fr0)) != B2C_OK) return rc;
+    CK(c, cudaEventRecord(c->ev_k[slot], c->s_main));
+    CK(c, cudaStreamWaitEvent(c->s_d2h, c->ev_k[slot], 0));
     uint8_t *hout = out_pinned ? edges_out + (size_t)f0 * out_frame_host : c->h_out[slot];
-    if (packed_bits) {
-      // the planes are shared between slots, so the D2H of the edge bit planes stays on the compute stream
-      for (int f = 0; f < cnt; ++f)
-        CK(c, cudaMemcpy2DAsync(hout + (size_t)f * out_frame_host, out_row, E0(c) + (size_t)f * plane_frame_stride(c), (size_t)c->plane_pitch * 4, out_row, h, cudaMemcpyDeviceToHost, c->s_main));
-      CK(c, cudaEventRecord(c->ev_k[slot], c->s_main));
-      CK(c, cudaEventRecord(c->ev_out[slot], c->s_main));
+    if (packed_bits) {   // the edge bit planes of the slot (rows are plane_pitch words apart, frames carry two ghost rows)
+      CK(c, cudaMemcpy2DAsync(hout, out_row, E0(c) + (long long)fr0 * plane_frame_stride(c), (size_t)c->plane_pitch * 4, out_row, (size_t)h, cudaMemcpyDeviceToHost, c->s_d2h));
+      for (int f = 1; f < cnt; ++f)
+        CK(c, cudaMemcpy2DAsync(hout + (size_t)f * out_frame_host, out_row, E0(c) + (long long)(fr0 + f) * plane_frame_stride(c), (size_t)c->plane_pitch * 4, out_row, (size_t)h, cudaMemcpyDeviceToHost,
+                                c->s_d2h));
+    } else if (c->edges_frame_stride == out_frame_host) {
+      CK(c, cudaMemcpyAsync(hout, dedges, (size_t)cnt * out_frame_host, cudaMemcpyDeviceToHost, c->s_d2h));
     } else {
-      CK(c, cudaEventRecord(c->ev_k[slot], c->s_main));
-      CK(c, cudaStreamWaitEvent(c->s_d2h, c->ev_k[slot], 0));
-      if (c->edges_frame_stride == out_frame_host) {
-        CK(c, cudaMemcpyAsync(hout, dedges, (size_t)cnt * out_frame_host, cudaMemcpyDeviceToHost, c->s_d2h));
-      } else {
-        for (int f = 0; f < cnt; ++f)
-          CK(c, cudaMemcpyAsync(hout + (size_t)f * out_frame_host, dedges + (size_t)f * c->edges_frame_stride, out_frame_host, cudaMemcpyDeviceToHost, c->s_d2h));
-      }
-      CK(c, cudaEventRecord(c->ev_out[slot], c->s_d2h));
-      // the next chunk that reuses this slot's edge half must wait for this D2H
-      CK(c, cudaStreamWaitEvent(c->s_main, c->ev_out[slot], 0));
+      for (int f = 0; f < cnt; ++f)
+        CK(c, cudaMemcpyAsync(hout + (size_t)f * out_frame_host, dedges + (size_t)f * c->edges_frame_stride, out_frame_host, cudaMemcpyDeviceToHost, c->s_d2h));
     }
+    CK(c, cudaEventRecord(c->ev_out[slot], c->s_d2h));
     pending_out[slot] = k;
   }
   for (int s = 0; s < nslots; ++s) {
@@ -728,7 +736,7 @@ int b2c_run_batch_host(b2c_handle c, const uint8_t *frames, size_t row_stride, i
     if (rc != B2C_OK) return rc;
   }
   CK(c, cudaStreamSynchronize(c->s_main));
-  c->last_in = c->d_in + (size_t)((nchunks - 1) % nslots) * slot_frames * c->in_frame_stride;
+  c->last_in = c->d_in + (size_t)c->acc_frame * c->in_frame_stride;   // (acc_frame = the last chunk's slot)
   c->last_row_stride = c->in_row_stride;
   c->have_frame = true;
   c->stages_valid = false;
@@ -764,11 +772,12 @@ int b2c_get_buffer(b2c_handle c, int id, const void **dev_ptr, size_t *pitch_byt
     }
   } else if (id == B2C_BUF_EDGES) {
     if (!c->edges_valid) return B2C_ERR_STATE;   // the last run stopped before the hysteresis
-    p = c->d_edges; pitch = c->edges_pitch;
+    p = c->d_edges + (size_t)c->acc_frame * c->edges_frame_stride; pitch = c->edges_pitch;
   } else if (id == B2C_BUF_MAP2) {
     if (!c->map2_valid) {   // the planes S and C are the map; this view is its accessor format
       if (!c->d_map2) CK(c, cudaMalloc(&c->d_map2, (size_t)c->rows_alloc * c->map_pitch * 4));
-      b2c::k_planes_to_map2<<<c->sm_count * 2, 256, 0, c->s_main>>>(reinterpret_cast<const uint16_t *>(S0(c)), reinterpret_cast<const uint16_t *>(C0(c)), c->plane_pitch * 2, c->d_map2,
+      b2c::k_planes_to_map2<<<c->sm_count * 2, 256, 0, c->s_main>>>(reinterpret_cast<const uint16_t *>(S0(c) + (long long)c->acc_frame * plane_frame_stride(c)),
+                                                                   reinterpret_cast<const uint16_t *>(C0(c) + (long long)c->acc_frame * plane_frame_stride(c)), c->plane_pitch * 2, c->d_map2,
                                                                    c->map_pitch, c->rows_alloc);
       CK(c, cudaGetLastError());
       c->launches++;
@@ -777,9 +786,9 @@ int b2c_get_buffer(b2c_handle c, int id, const void **dev_ptr, size_t *pitch_byt
     p = c->d_map2; pitch = (size_t)c->map_pitch * 4; es = 4;
   } else if (id == B2C_BUF_BITS) {
     if (!c->edges_valid) return B2C_ERR_STATE;
-    p = E0(c); pitch = (size_t)c->plane_pitch * 4; es = 4;
+    p = E0(c) + (long long)c->acc_frame * plane_frame_stride(c); pitch = (size_t)c->plane_pitch * 4; es = 4;
   } else if (id == B2C_BUF_VIEW) {
-    if (c->last_stage == B2C_STAGE_HYSTER) { p = c->d_edges; pitch = c->edges_pitch; }
+    if (c->last_stage == B2C_STAGE_HYSTER) { p = c->d_edges + (size_t)c->acc_frame * c->edges_frame_stride; pitch = c->edges_pitch; }
     else { p = c->d_view; pitch = (size_t)c->w; }
   } else {
     return B2C_ERR_INVALID;
@@ -1318,6 +1327,49 @@ int b2c_device_count(void)
   return n;
 }
 long long b2c_launch_count(b2c_handle c) { return c ? c->launches : 0; }
+
+// Binds the calling thread (and the threads it starts later) to the CPUs of the NUMA node the GPU hangs on, so that the
+// pinned frame rings allocated afterwards (first touch) and the staging memcpys are local to the GPU's PCIe root.  Linux
+// sysfs; returns the node, or -1 if the platform does not say (nothing is changed then).
+int b2c_bind_host_to_device(int device)
+{
+  char bus[32] = { 0 };
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return -1;
+  }
+  for (char *q = bus; *q; ++q) *q = (char)tolower((unsigned char)*q);
+  char path[128];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE *f = fopen(path, "r");
+  if (!f) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  if (node < 0) return -1;
+  snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+  f = fopen(path, "r");
+  if (!f) return -1;
+  char list[4096] = { 0 };
+  const bool ok = fgets(list, sizeof(list), f) != nullptr;
+  fclose(f);
+  if (!ok) return -1;
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  int count = 0;
+  for (char *q = list; *q;) {   // "0-55,112-167"
+    char *e;
+    const long a = strtol(q, &e, 10);
+    if (e == q) break;
+    long b = a;
+    if (*e == '-') b = strtol(e + 1, &e, 10);
+    for (long k = a; k <= b && k < CPU_SETSIZE; ++k) { CPU_SET((int)k, &set); ++count; }
+    q = (*e == ',') ? e + 1 : e;
+    if (*e != ',') break;
+  }
+  if (count == 0 || sched_setaffinity(0, sizeof(set), &set) != 0) return -1;
+  return node;
+}
 
 int b2c_set_option(b2c_handle c, const char *name, int value)
 {

@@ -100,8 +100,9 @@ B2C_API int b2c_hysteresis_device(b2c_handle h, int n, uint8_t *dev_edges, size_
  * b2c_hysteresis_device(h, 1, ...) or, on a band handle, b2c_band_hysteresis.  Blocking. */
 B2C_API int b2c_load_thresh(b2c_handle h, const uint8_t *host_thresh, size_t row_stride);
 
-/* ---- batch of host frames through the pinned, double-buffered async pipeline (H2D / kernels / D2H
- * overlapped on separate streams).  frames = n contiguous frames of row_stride*height bytes;
+/* ---- batch of host frames through the pinned async pipeline: the handle's batch buffers are cut into up to 8 slots of
+ * at most 8 frames; upload, kernels and download of successive chunks overlap on three streams, so only the first
+ * small upload and the last small download are exposed.  frames = n contiguous frames of row_stride*height bytes;
  * edges_out receives n tightly packed w*h maps (or, with packed_bits != 0, n bit maps of
  * ceil(w/32)*4 bytes per row).  Blocking until the last frame is back.  Replaces the per-frame
  * blocking upload + PBO copy of cannyEdgeH.cu:122-212 for streams of frames. */
@@ -180,6 +181,10 @@ B2C_API const char *b2c_strerror(int status);
 B2C_API const char *b2c_last_cuda_error(b2c_handle h);
 B2C_API const char *b2c_version(void);
 B2C_API int b2c_device_count(void);
+/* Host placement for one process per GPU on multi-socket boxes: binds the calling thread to the CPUs of the NUMA node
+ * the GPU hangs on (Linux sysfs), so that pinned rings allocated afterwards and the staging copies are local to the
+ * GPU's PCIe root.  Returns the node, or -1 if unknown (nothing changed). */
+B2C_API int b2c_bind_host_to_device(int device);
 /* kernels launched by this handle since creation (bench.py reports it as gpu_launches) */
 B2C_API long long b2c_launch_count(b2c_handle h);
 /* options: "stencil_impl" 0 = marching kernel (default), 1 = staged tile kernel (the all-stages path of the
