@@ -38,6 +38,7 @@ _SIGS = {
     "b2c_run_batch_host": (_i, [_vp, _u8p, _sz, _i, _u8p, _i]),
     "b2c_get_buffer": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_sz), C.POINTER(_i)]),
     "b2c_download": (_i, [_vp, _i, _vp, _sz]),
+    "b2c_copy_view": (_i, [_vp, _vp, _sz, _vp]),
     "b2c_dev_alloc": (_i, [_vp, _sz, C.POINTER(_vp)]),
     "b2c_dev_free": (_i, [_vp, _vp]),
     "b2c_dev_upload": (_i, [_vp, _vp, _vp, _sz]),

@@ -101,6 +101,11 @@ class CannyEdge:
             raise _lib.B2cError(_lib.ERR_SIZE, what="run")
         check(lib.b2c_run(self._h, f.ctypes.data, f.strides[0], int(final_stage)), self._h, "b2c_run")
 
+    def copy_view(self, dev_dst, pitch=0, stream=None):
+        """The GL-free half of _sendOutputToOpenGL (cannyEdgeH.cu:154-212): the u8 picture of the stage the last run stopped
+        at, device to device into dev_dst (an int address, e.g. a mapped PBO), rows `pitch` bytes apart (0 = width)."""
+        check(lib.b2c_copy_view(self._h, dev_dst, pitch, stream), self._h, "b2c_copy_view")
+
     def run_device(self, dev_ptr, row_stride, frame_stride, n, edges_ptr=None, edges_pitch=0, edges_frame_stride=0, stream=None):
         check(lib.b2c_run_device(self._h, dev_ptr, row_stride, frame_stride, n, edges_ptr, edges_pitch, edges_frame_stride, stream), self._h, "b2c_run_device")
 

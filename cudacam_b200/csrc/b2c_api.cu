@@ -819,6 +819,29 @@ int b2c_download(b2c_handle c, int id, void *host, size_t host_pitch)
   return B2C_OK;
 }
 
+// The reference's _sendOutputToOpenGL (cannyEdgeH.cu:154-212) without the GL part: the selected stage's u8 picture of
+// the last run (for GRADIENT the saturated float2uchar view, cannyEdgeD.cu:35-50) copied device-to-device into the
+// caller's buffer -- the pointer cudaGraphicsResourceGetMappedPointer returned for the PBO (tight pitch = width there,
+// cannyEdgeH.cu:172,188-207).  Asynchronous on `stream` (0 = the handle's compute stream).
+int b2c_copy_view(b2c_handle c, void *dev_dst, size_t dst_pitch, void *stream)
+{
+  if (!c || !dev_dst || c->band) return B2C_ERR_INVALID;
+  if (dst_pitch == 0) dst_pitch = (size_t)c->w;
+  if (dst_pitch < (size_t)c->w) return B2C_ERR_SIZE;
+  const void *p;
+  size_t pitch;
+  int rc = b2c_get_buffer(c, B2C_BUF_VIEW, &p, &pitch, nullptr);
+  if (rc != B2C_OK) return rc;
+  DevGuard g(c->dev);
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->s_main;
+  if (st != c->s_main) {   // the view was produced on the handle's stream
+    CK(c, cudaEventRecord(c->ev_k[0], c->s_main));   // (an event of the host pipeline, idle outside b2c_run_batch_host)
+    CK(c, cudaStreamWaitEvent(st, c->ev_k[0], 0));
+  }
+  CK(c, cudaMemcpy2DAsync(dev_dst, dst_pitch, p, pitch, (size_t)c->w, c->rows_alloc, cudaMemcpyDeviceToDevice, st));
+  return B2C_OK;
+}
+
 int b2c_dev_alloc(b2c_handle c, size_t bytes, void **dev_ptr)
 {
   if (!c || !dev_ptr) return B2C_ERR_INVALID;
@@ -869,6 +892,10 @@ int b2c_sync(b2c_handle c)
 {
   if (!c) return B2C_ERR_INVALID;
   DevGuard g(c->dev);
+  if (c->band) {   // a band's work may sit on the caller's stream and on the side stream of the pushes
+    CK(c, cudaDeviceSynchronize());
+    return B2C_OK;
+  }
   CK(c, cudaStreamSynchronize(c->s_main));
   CK(c, cudaStreamSynchronize(c->s_h2d));
   CK(c, cudaStreamSynchronize(c->s_d2h));

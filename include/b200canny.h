@@ -113,6 +113,11 @@ B2C_API int b2c_run_batch_host(b2c_handle h, const uint8_t *frames, size_t row_s
  * fused path did not write are produced on demand from the retained input. */
 B2C_API int b2c_get_buffer(b2c_handle h, int buffer_id, const void **dev_ptr, size_t *pitch_bytes, int *elem_size);
 B2C_API int b2c_download(b2c_handle h, int buffer_id, void *host, size_t host_pitch_bytes);
+/* The GL-free half of _sendOutputToOpenGL (cannyEdgeH.cu:154-212): the u8 picture of the stage the last run stopped at
+ * (GRADIENT: the saturated float2uchar view) copied device-to-device into dev_dst, rows dst_pitch bytes apart (0 = width,
+ * the PBO layout of imguiApp.cpp:76).  dev_dst is what cudaGraphicsResourceGetMappedPointer gave the caller for its PBO.
+ * Asynchronous on `stream` (0 = the handle's compute stream). */
+B2C_API int b2c_copy_view(b2c_handle h, void *dev_dst, size_t dst_pitch, void *stream);
 
 /* ---- device memory helpers so that non-CUDA hosts can keep frames resident */
 B2C_API int b2c_dev_alloc(b2c_handle h, size_t bytes, void **dev_ptr);

@@ -137,10 +137,37 @@ def test_strided_input_and_threshold_api():
         assert c.isKernelProfilingEnabled()                               # default ON: cannyEdgeH.cu:24
         c.run(view)
         assert np.array_equal(c.edges(), O.canny(f)["edges"])
-        t = c.lastTimings()
-        assert t["total"] > 0 and t["rounds"] >= 1
+        t = c.lastTimings()   # event marks upload | stencil | hysteresis | output tile the total
+        assert all(t[k] > 0 for k in ("upload", "stencil", "hysteresis", "output", "total")) and t["rounds"] == 1
+        assert abs(t["upload"] + t["stencil"] + t["hysteresis"] + t["output"] - t["total"]) <= 0.02 * t["total"] + 0.005
+        c.enableKernelProfiling(False)
+        c.run(view)
+        with pytest.raises(cb.B2cError):   # no marks were recorded for that run
+            c.lastTimings()
+        c.enableKernelProfiling(True)
         with pytest.raises(cb.B2cError):
             c.run(np.zeros((h + 1, w, 3), np.uint8))
+
+
+def test_copy_view_is_the_pbo_copy():
+    """b2c_copy_view = the D2D copy of cannyEdgeH.cu:188-207 into a caller-owned device buffer (the mapped PBO), for the
+    edge map and for the saturated gradient view, with a pitch of its own."""
+    import torch
+    w, h = 333, 222
+    f = synth.frame("steps", 4, w, h)
+    r = O.canny(f)
+    with cb.CannyEdge(w, h) as c:
+        for stage, want in ((cb.CannyStage.HYSTER, r["edges"]), (cb.CannyStage.GRADIENT, O.float2uchar(r["grad"])), (cb.CannyStage.GAUSSIAN, r["blur"])):
+            c.run(f, stage)
+            for pitch in (0, 352):
+                dst = torch.full((h, pitch or w), 7, dtype=torch.uint8, device="cuda")
+                c.copy_view(dst.data_ptr(), pitch)
+                c.sync()
+                got = dst.cpu().numpy()
+                assert np.array_equal(got[:, :w], want) and np.array_equal(got[:, :w], c.view())
+                assert (got[:, w:] == 7).all()
+        with pytest.raises(cb.B2cError):
+            c.copy_view(dst.data_ptr(), w - 1)
 
 
 def test_cvpipeline_surface():
