@@ -100,7 +100,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.02)   # (NVML queries take a driver lock: polling harder than this slows the launches of all ranks)
 
     def start(self):
         if self.nv and os.environ.get("B2C_NO_SAMPLER", "0") != "1":

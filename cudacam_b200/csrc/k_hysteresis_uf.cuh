@@ -174,30 +174,40 @@ __global__ void __launch_bounds__(UT_THREADS) k_uf_tile(const B2cHystParams p, u
   const int wpr = (p.w + 31) >> 5;
   const int f = blockIdx.z, y0 = blockIdx.y * UT_ROWS, xw0 = blockIdx.x * UT_WORDS;
   if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) { p.flags[3] = 1; p.flags[4] = 0; }
-  {   // ---- phase 0, one thread per plane word: S / C planes, tile copies, compaction of the words with weak pixels
-    const int ly = tid >> 3, lw = tid & 7, y = y0 + ly, xw = xw0 + lw;
-    uint32_t wd = 0u, sM = 0u;
+  // ---- phase 0: S / C planes -> tile copies + compacted list of the words with weak pixels.  Two warps do it with
+  // 128-bit loads (thread = 4 consecutive words of one tile row; rows are 16-byte aligned, words past the image are zero
+  // padding), the other six go straight to the barrier: with one word per thread this phase alone was ~90 instructions
+  // in each of the 8 warps of every tile, and the kernel is issue-bound on it.
+  if (tid < 2 * UT_ROWS) {
+    const int ly = tid >> 1, lw = 4 * (tid & 1), y = y0 + ly, xw = xw0 + lw;
+    uint4 sv = make_uint4(0u, 0u, 0u, 0u), cv = sv;
     if (y < p.h && xw < wpr) {   // the planes were written by the stencil kernel: S = strong, C = weak | strong
       const long long o = f * p.plane_frame_stride + (long long)y * p.plane_pitch + xw;
-      sM = p.S[o];
-      wd = p.C[o] & ~sM;
+      sv = *reinterpret_cast<const uint4 *>(p.S + o);
+      cv = *reinterpret_cast<const uint4 *>(p.C + o);
     }
-    LW[tid] = wd;
-    LS[tid] = sM;
-    const uint32_t mask = __ballot_sync(B2C_FULL, wd != 0u);
-    if (lane == 0) WC[warp] = __popc(mask);
-    __syncthreads();
-    // prefix over the 8 warp counts: lane w reads count w, two ballot-free shuffles give "before" and the total
-    int cw = lane < UT_THREADS / 32 ? WC[lane] : 0, total = cw, before;
-#pragma unroll
-    for (int d = 1; d < UT_THREADS / 32; d <<= 1) {
-      const int v = __shfl_up_sync(B2C_FULL, total, d);
-      if (lane >= d) total += v;
-    }
-    before = __shfl_sync(B2C_FULL, total - cw, warp);
-    total = __shfl_sync(B2C_FULL, total, UT_THREADS / 32 - 1);
-    if (wd) IT[before + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)tid;
-    if (tid == 0) WC[UT_THREADS / 32] = total;
+    const uint4 wv = make_uint4(cv.x & ~sv.x, cv.y & ~sv.y, cv.z & ~sv.z, cv.w & ~sv.w);
+    const int t0 = ly * UT_WORDS + lw;   // tile position of the first of the 4 words
+    *reinterpret_cast<uint4 *>(LW + t0) = wv;
+    *reinterpret_cast<uint4 *>(LS + t0) = sv;
+    // list position of (lane, k): words k of all lanes, then words k+1 ... (any order serves)
+    const unsigned m0 = __ballot_sync(B2C_FULL, wv.x != 0u), m1 = __ballot_sync(B2C_FULL, wv.y != 0u), m2 = __ballot_sync(B2C_FULL, wv.z != 0u),
+                   m3 = __ballot_sync(B2C_FULL, wv.w != 0u);
+    const int n0 = __popc(m0), n1 = __popc(m1), n2 = __popc(m2), n3 = __popc(m3), mine = n0 + n1 + n2 + n3;
+    if (lane == 0) WC[warp] = mine;
+    // (both warps are past their ballots before either reads the other's count: named barrier over the two warps)
+#ifdef B2C_EMU
+    emu::named_bar_sync(1, 64);
+#else
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+#endif
+    const int before = warp == 0 ? 0 : WC[0];
+    const unsigned lt = (1u << lane) - 1u;
+    if (wv.x) IT[before + __popc(m0 & lt)] = (uint16_t)t0;
+    if (wv.y) IT[before + n0 + __popc(m1 & lt)] = (uint16_t)(t0 + 1);
+    if (wv.z) IT[before + n0 + n1 + __popc(m2 & lt)] = (uint16_t)(t0 + 2);
+    if (wv.w) IT[before + n0 + n1 + n2 + __popc(m3 & lt)] = (uint16_t)(t0 + 3);
+    if (tid == 32) WC[UT_THREADS / 32] = before + mine;   // warp 1 knows the total
   }
   __syncthreads();
   const int nitems = WC[UT_THREADS / 32];
