@@ -232,3 +232,20 @@ def test_other_input_formats(ch, impl):
         _check_all(c, g, r)
         got = c.run_batch(np.stack([g, g, g]))
         assert np.array_equal(got[1], r["edges"])
+
+
+def test_nv12_luma_plane():
+    """NV12 camera frames: the luma plane is the gray picture -- the GRAY8 front end on the Y plane with
+    the surface's pitch; the interleaved chroma plane behind it is never read."""
+    w, h, pitch = 1000, 562, 1024
+    f = synth.frame("scene", 17, w, h)
+    y = ((f[:, :, 0].astype(np.uint32) * 7 + f[:, :, 1].astype(np.uint32) * 38 + f[:, :, 2].astype(np.uint32) * 19) >> 6).astype(np.uint8)
+    nv12 = np.full((h + h // 2, pitch), 0x5A, np.uint8)   # Y rows, then the UV rows (garbage here)
+    nv12[:h, :w] = y
+    luma = np.lib.stride_tricks.as_strided(nv12, (h, w, 1), (pitch, 1, 1))
+    r = O.canny(np.ascontiguousarray(y[:, :, None]))
+    with cb.CannyEdge(w, h, channels=1) as c:
+        c.run(luma)
+        assert np.array_equal(c.edges(), r["edges"]) and np.array_equal(c.mono(), y)
+    # and it is what the BGR path computes from the same picture (gray = (7B + 38G + 19R) >> 6, cannyEdgeD.cu:14-19)
+    assert np.array_equal(r["edges"], O.canny(f)["edges"])
