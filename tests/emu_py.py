@@ -9,6 +9,9 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 EMU_DIR = os.path.join(HERE, "emu")
 EMU_SO = os.path.join(EMU_DIR, "libemu.so")
+# B2C_EMU_SO=/path/to/libemu_asan.so (built by tools/emu_asan.sh with -fsanitize=address, run under LD_PRELOAD=libasan)
+# turns the emulator tests into an out-of-bounds check of the kernels' indexing: compute-sanitizer is closed on the GPU pool
+EMU_OVERRIDE = os.environ.get("B2C_EMU_SO")
 _vp, _i, _ll = C.c_void_p, C.c_int, C.c_longlong
 
 
@@ -28,8 +31,9 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        build()
-        _lib = C.CDLL(EMU_SO)
+        if not EMU_OVERRIDE:
+            build()
+        _lib = C.CDLL(EMU_OVERRIDE or EMU_SO)
         _lib.emu_stencil.restype = _i
         _lib.emu_stencil.argtypes = [_i, _vp, _ll, _ll, _i, _i, _i, _i, _i, C.c_uint, C.c_uint, _vp, _vp, _vp, _vp, _vp, _vp]
         _lib.emu_set_channels.restype = None
