@@ -37,11 +37,18 @@ CANNY_STAGES = {
 }
 
 
+PLANAR_BGR8 = 0x103   # include/b200canny.h B2C_PLANAR_BGR8
+
+
 class CannyEdge:
-    def __init__(self, width, height, channels=3, device=0, max_batch=1):
+    def __init__(self, width, height, channels=3, device=0, max_batch=1, planar=False):
+        """planar=True (with channels=3): frames are three planes B, G, R -- arrays of shape (3, h, w)."""
         self.width, self.height, self.channels, self.device, self.max_batch = width, height, channels, device, max_batch
+        self.planar = bool(planar)
+        if self.planar and channels != 3:
+            raise ValueError("planar input is BGR8")
         h = C.c_void_p()
-        check(lib.b2c_create(C.byref(h), device, width, height, channels, max_batch), what="b2c_create")
+        check(lib.b2c_create(C.byref(h), device, width, height, PLANAR_BGR8 if self.planar else channels, max_batch), what="b2c_create")
         self._h = h
 
     # -- lifetime ------------------------------------------------------------------------------------------
@@ -92,6 +99,11 @@ class CannyEdge:
         """frame: (h, w, channels) uint8 host array -- BGR8, BGRA8 or GRAY8 ((h, w) also accepted) as given to the
         constructor; rows may be strided, like cv::Mat::step."""
         f = np.asarray(frame)
+        if self.planar:   # (3, h, w): planes B, G, R, rows may be strided, planes must follow each other
+            if f.dtype != np.uint8 or f.shape != (3, self.height, self.width) or f.strides[2] != 1 or f.strides[0] != f.strides[1] * self.height:
+                raise ValueError("planar frame must be a (3, h, w) uint8 array of consecutive planes")
+            check(lib.b2c_run(self._h, f.ctypes.data, f.strides[1], int(final_stage)), self._h, "b2c_run")
+            return
         if f.ndim == 2:
             f = f[:, :, None]
         ch = self.channels
@@ -112,12 +124,13 @@ class CannyEdge:
     def run_batch(self, frames, packed_bits=False, out=None):
         """frames: (n, h, w, channels) uint8 host array -> (n, h, w) uint8 edge maps (or (n, h, ceil(w/32)) uint32 bit maps)."""
         f = np.asarray(frames)
-        if f.dtype != np.uint8 or f.ndim != 4 or f.shape[1:] != (self.height, self.width, self.channels) or not f.flags.c_contiguous:
-            raise ValueError("frames must be a C-contiguous (n, h, w, channels) uint8 array")
+        shape = (3, self.height, self.width) if self.planar else (self.height, self.width, self.channels)
+        if f.dtype != np.uint8 or f.ndim != 4 or f.shape[1:] != shape or not f.flags.c_contiguous:
+            raise ValueError("frames must be a C-contiguous (n, h, w, channels) -- planar: (n, 3, h, w) -- uint8 array")
         n = f.shape[0]
         if out is None:
             out = np.empty((n, self.height, (self.width + 31) // 32), np.uint32) if packed_bits else np.empty((n, self.height, self.width), np.uint8)
-        check(lib.b2c_run_batch_host(self._h, f.ctypes.data, self.width * self.channels, n, out.ctypes.data, 1 if packed_bits else 0), self._h, "b2c_run_batch_host")
+        check(lib.b2c_run_batch_host(self._h, f.ctypes.data, self.width * (1 if self.planar else self.channels), n, out.ctypes.data, 1 if packed_bits else 0), self._h, "b2c_run_batch_host")
         return out
 
     # -- accessors ----------------------------------------------------------------------------------------------

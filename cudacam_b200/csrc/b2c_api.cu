@@ -61,6 +61,9 @@ struct b2c_ctx {
   int plane_pitch = 0;    // u32 per row of a bit plane (allocated)
   int rows_alloc = 0;     // rows per frame of map / planes / edges (h, or band rows)
   size_t in_row_stride = 0, in_frame_stride = 0;   // own input buffer
+  bool planar = false;      // B2C_PLANAR_BGR8: three planes (B, G, R) of `height` rows each instead of interleaved pixels
+  size_t row_bytes() const { return planar ? (size_t)w : (size_t)w * ch; }   // payload bytes of one input row
+  int rows_in() const { return planar ? 3 * h : h; }                         // input rows per frame
   size_t edges_pitch = 0, edges_frame_stride = 0;
   int pitch8 = 0, pitchf = 0;   // stage buffers, elements
 
@@ -234,6 +237,7 @@ void fill_stencil_params(b2c_ctx *c, B2cStencilParams &p, const uint8_t *bgr, si
   p.h_glob = c->band ? c->h_glob : c->h;
   p.nframes = n;
   p.channels = c->ch;
+  p.plane_stride = c->planar ? (long long)row_stride * c->rows_alloc : 0;
   p.pl_S = reinterpret_cast<uint16_t *>(S0(c) + (long long)frame0 * plane_frame_stride(c));
   p.pl_C = reinterpret_cast<uint16_t *>(C0(c) + (long long)frame0 * plane_frame_stride(c));
   p.pl_pitch16 = c->plane_pitch * 2;
@@ -365,7 +369,9 @@ int b2c_create(b2c_handle *out, int device, int width, int height, int channels,
 {
   if (!out || width < 1 || height < 1 || max_batch < 1) return B2C_ERR_INVALID;
   *out = nullptr;
-  if (channels != 3 && channels != 1 && channels != 4) return B2C_ERR_UNSUPPORTED;   // BGR8, GRAY8, BGRA8
+  const bool planar = channels == B2C_PLANAR_BGR8;
+  if (planar) channels = 3;
+  if (channels != 3 && channels != 1 && channels != 4) return B2C_ERR_UNSUPPORTED;   // BGR8 (interleaved or planar), GRAY8, BGRA8
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
     (void)cudaGetLastError();
@@ -380,8 +386,9 @@ int b2c_create(b2c_handle *out, int device, int width, int height, int channels,
   c->max_batch = max_batch;
   c->rows_alloc = height;
   DevGuard g(device);
-  c->in_row_stride = round_up(round_up((size_t)width, 8) * channels, 16);   // whole 8-pixel lanes are backed by memory
-  c->in_frame_stride = c->in_row_stride * height;
+  c->planar = planar;
+  c->in_row_stride = planar ? round_up((size_t)width, 16) : round_up(round_up((size_t)width, 8) * channels, 16);   // whole 8-pixel lanes are backed by memory
+  c->in_frame_stride = c->in_row_stride * c->rows_in();
   int rc = alloc_common(c);
   if (rc == B2C_OK && cudaMalloc(&c->d_in, (size_t)max_batch * c->in_frame_stride) != cudaSuccess) rc = set_err(c, cudaGetLastError(), "cudaMalloc(d_in)");
   if (rc != B2C_OK) {
@@ -541,12 +548,12 @@ int b2c_run(b2c_handle c, const uint8_t *host_bgr, size_t row_stride, int final_
 {
   if (!c || !host_bgr || c->band) return B2C_ERR_INVALID;
   if (final_stage < B2C_STAGE_MONO || final_stage > B2C_STAGE_HYSTER) return B2C_ERR_INVALID;
-  if (row_stride < (size_t)c->w * c->ch) return B2C_ERR_SIZE;
+  if (row_stride < c->row_bytes()) return B2C_ERR_SIZE;
   DevGuard g(c->dev);
   cudaStream_t st = c->s_main;
   const bool prof = c->profiling;
   if (prof) CK(c, cudaEventRecord(c->ev_t[0], st));
-  CK(c, cudaMemcpy2DAsync(c->d_in, c->in_row_stride, host_bgr, row_stride, (size_t)c->w * c->ch, c->h, cudaMemcpyHostToDevice, st));
+  CK(c, cudaMemcpy2DAsync(c->d_in, c->in_row_stride, host_bgr, row_stride, c->row_bytes(), c->rows_in(), cudaMemcpyHostToDevice, st));
   if (prof) CK(c, cudaEventRecord(c->ev_t[1], st));
   c->last_in = c->d_in;
   c->last_row_stride = c->in_row_stride;
@@ -586,7 +593,7 @@ int b2c_run(b2c_handle c, const uint8_t *host_bgr, size_t row_stride, int final_
 int b2c_run_device(b2c_handle c, const uint8_t *dev_bgr, size_t row_stride, size_t frame_stride, int n, uint8_t *dev_edges, size_t edges_pitch, size_t edges_frame_stride, void *stream)
 {
   if (!c || !dev_bgr || c->band || n < 1 || n > c->max_batch) return B2C_ERR_INVALID;
-  if (row_stride < (size_t)c->w * c->ch) return B2C_ERR_SIZE;
+  if (row_stride < c->row_bytes()) return B2C_ERR_SIZE;
   DevGuard g(c->dev);
   cudaStream_t st = stream ? (cudaStream_t)stream : c->s_main;
   if (!dev_edges) {
@@ -621,7 +628,7 @@ int b2c_run_device(b2c_handle c, const uint8_t *dev_bgr, size_t row_stride, size
 int b2c_stencil_device(b2c_handle c, const uint8_t *dev_bgr, size_t row_stride, size_t frame_stride, int n, void *stream)
 {
   if (!c || !dev_bgr || c->band || n < 1 || n > c->max_batch) return B2C_ERR_INVALID;
-  if (row_stride < (size_t)c->w * c->ch) return B2C_ERR_SIZE;
+  if (row_stride < c->row_bytes()) return B2C_ERR_SIZE;
   DevGuard g(c->dev);
   return launch_stencil(c, dev_bgr, row_stride, frame_stride, n, stream ? (cudaStream_t)stream : c->s_main);
 }
@@ -641,7 +648,7 @@ int b2c_hysteresis_device(b2c_handle c, int n, uint8_t *dev_edges, size_t edges_
 int b2c_run_batch_host(b2c_handle c, const uint8_t *frames, size_t row_stride, int n, uint8_t *edges_out, int packed_bits)
 {
   if (!c || !frames || !edges_out || c->band || n < 1) return B2C_ERR_INVALID;
-  if (row_stride < (size_t)c->w * c->ch) return B2C_ERR_SIZE;
+  if (row_stride < c->row_bytes()) return B2C_ERR_SIZE;
   DevGuard g(c->dev);
   const int w = c->w, h = c->h;
   // The batch buffers of the handle (input, planes, forest, edge maps: max_batch frames each) are cut into up to NSLOT
@@ -649,7 +656,7 @@ int b2c_run_batch_host(b2c_handle c, const uint8_t *frames, size_t row_stride, i
   // download on s_d2h.  With 8-frame chunks only the first upload and the last download are not hidden.
   const int slot_frames = std::max(1, std::min(SLOT_FRAMES, (c->max_batch + 1) / 2));
   const int nslots = std::max(1, std::min(NSLOT, c->max_batch / slot_frames));
-  const size_t in_frame_host = row_stride * h;
+  const size_t in_frame_host = row_stride * c->rows_in();
   const size_t out_row = packed_bits ? (size_t)c->wpr * 4 : (size_t)w;
   const size_t out_frame_host = out_row * h;
 
@@ -706,7 +713,7 @@ int b2c_run_batch_host(b2c_handle c, const uint8_t *frames, size_t row_stride, i
       CK(c, cudaMemcpyAsync(din, src, (size_t)cnt * in_frame_host, cudaMemcpyHostToDevice, c->s_h2d));
     } else {
       for (int f = 0; f < cnt; ++f)
-        CK(c, cudaMemcpy2DAsync(din + (size_t)f * c->in_frame_stride, c->in_row_stride, src + (size_t)f * in_frame_host, row_stride, (size_t)w * c->ch, h, cudaMemcpyHostToDevice, c->s_h2d));
+        CK(c, cudaMemcpy2DAsync(din + (size_t)f * c->in_frame_stride, c->in_row_stride, src + (size_t)f * in_frame_host, row_stride, c->row_bytes(), c->rows_in(), cudaMemcpyHostToDevice, c->s_h2d));
     }
     CK(c, cudaEventRecord(c->ev_in[slot], c->s_h2d));
 

@@ -43,6 +43,8 @@ struct B2cStencilParams {
                              // outside [0,h_glob), real neighbour rows are read inside it)
   int nframes;
   int channels;              // bytes per input pixel: 3 = BGR8, 4 = BGRA8 (alpha ignored), 1 = GRAY8
+  long long plane_stride;    // 0 = interleaved pixels; else planar BGR8: bytes from the B plane to the G plane to the R plane
+                             // (channels = 3, row_stride = bytes per plane row; tile kernel only)
   // out: the two bit planes of the 2-bit weak/strong map, as 16-bit halves (one u16 per 16 pixels: strips are 15
   // such groups wide): S = strong, C = weak | strong; row 0 of frame 0
   uint16_t *pl_S, *pl_C;

@@ -792,7 +792,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, MARCH_CTAS_PER_SM) k_stencil_ma
 #ifdef B2C_EMU
 inline bool march_supported(const B2cStencilParams &p)
 {
-  return p.w >= 8 && p.row_stride % 8 == 0 && p.frame_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(p.bgr) & 7) == 0 &&
+  return p.plane_stride == 0 && p.w >= 8 && p.row_stride % 8 == 0 && p.frame_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(p.bgr) & 7) == 0 &&
          p.row_stride >= (long long)((p.w + 7) / 8 * 8) * p.channels;
 }
 inline int march_emu_launch(const B2cStencilParams &p, int rb)
@@ -823,7 +823,7 @@ inline cudaError_t march_configure(int *ctas_per_sm)
 // Anything else goes through the tile kernel.
 inline bool march_supported(const B2cStencilParams &p)
 {
-  return p.w >= 8 && p.row_stride % 8 == 0 && p.frame_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(p.bgr) & 7) == 0 &&
+  return p.plane_stride == 0 && p.w >= 8 && p.row_stride % 8 == 0 && p.frame_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(p.bgr) & 7) == 0 &&
          p.row_stride >= (long long)((p.w + 7) / 8 * 8) * p.channels;
 }
 // Rows per band.  Bands of 12k-4 rows waste no block (a band of rb rows runs ceil((rb+4)/12) blocks of 12 rows).

@@ -45,8 +45,13 @@ __global__ void __launch_bounds__(TILE_THREADS) k_stencil_tile(const B2cStencilP
     unsigned v = 0;
     // (rows past the 4 halo rows below the band / frame feed no stored pixel and may lie outside the caller's buffer)
     if (x >= 0 && x < p.w && yg >= 0 && yg < p.h_glob && y < p.h + 4) {
-      const uint8_t *q = src + (long long)y * p.row_stride + p.channels * x;
-      v = p.channels == 1 ? q[0] : (q[0] * 7u + q[1] * 38u + q[2] * 19u) >> 6;   // BGR8 / BGRA8 (alpha ignored) / GRAY8
+      if (p.plane_stride) {   // planar BGR8
+        const uint8_t *q = src + (long long)y * p.row_stride + x;
+        v = (q[0] * 7u + q[p.plane_stride] * 38u + q[2 * p.plane_stride] * 19u) >> 6;
+      } else {
+        const uint8_t *q = src + (long long)y * p.row_stride + p.channels * x;
+        v = p.channels == 1 ? q[0] : (q[0] * 7u + q[1] * 38u + q[2] * 19u) >> 6;   // BGR8 / BGRA8 (alpha ignored) / GRAY8
+      }
     }
     s_mono[i] = (uint8_t)v;
   }

@@ -62,7 +62,11 @@ enum {
 /* ---- lifetime: cvp::cuda::CannyEdge::CannyEdge / ~CannyEdge (cannyEdgeH.cu:16-47), _initAlloc/_endAlloc (:340-407)
  * channels = bytes per pixel of the input frames: 3 = BGR8 (what the reference processes), 4 = BGRA8 (alpha ignored),
  * 1 = GRAY8 (the gray value is the byte: what the reference's CV_8UC1 path evidently meant to do -- upstream it
- * uploads the frame to d_mono and then overwrites it with rgb2mono of a stale d_rgb, cannyEdgeH.cu:140-146 + :60-64). */
+ * uploads the frame to d_mono and then overwrites it with rgb2mono of a stale d_rgb, cannyEdgeH.cu:140-146 + :60-64);
+ * NV12 surfaces use it on their luma plane), B2C_PLANAR_BGR8 = three planes B, G, R of `height` rows each instead of
+ * interleaved pixels (row_stride = bytes per plane row, frame = 3 * height rows; served by the staged tile kernel, not
+ * by the fast marching kernel). */
+#define B2C_PLANAR_BGR8 0x103
 B2C_API int b2c_create(b2c_handle *out, int device, int width, int height, int channels, int max_batch);
 B2C_API void b2c_destroy(b2c_handle h);
 

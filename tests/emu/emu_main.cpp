@@ -23,8 +23,10 @@ static void fill_gk(float gk[25])
 }
 
 static int g_emu_channels = 3;
+static long long g_emu_plane_stride = 0;
 extern "C" {
 __attribute__((visibility("default"))) void emu_set_channels(int ch) { g_emu_channels = ch; }
+__attribute__((visibility("default"))) void emu_set_plane_stride(long long s) { g_emu_plane_stride = s; }   // planar BGR8 (tile kernel)
 // impl: 1 = tile kernel (EMIT when any stage pointer is given), 100 + rb = marching kernel with rb rows per band
 __attribute__((visibility("default"))) int emu_stencil(int impl, const uint8_t *bgr, long long row_stride, long long frame_stride, int w, int h, int y0, int h_glob, int nframes,
                                                        unsigned lo, unsigned hi, uint32_t *map2, uint8_t *mono, uint8_t *blur, float *grad, uint8_t *nms, uint8_t *thresh)
@@ -34,7 +36,7 @@ __attribute__((visibility("default"))) int emu_stencil(int impl, const uint8_t *
   alignas(16) static const uint8_t zeros[256] = { 0 };
   p.zeros = zeros;
   p.bgr = bgr; p.row_stride = row_stride; p.frame_stride = frame_stride;
-  p.w = w; p.h = h; p.y0 = y0; p.h_glob = h_glob; p.nframes = nframes; p.channels = g_emu_channels;
+  p.w = w; p.h = h; p.y0 = y0; p.h_glob = h_glob; p.nframes = nframes; p.channels = g_emu_channels; p.plane_stride = g_emu_plane_stride;
   // the kernels write the bit planes S and C; the tests look at the 2-bit map view
   const int gpr = (w + 15) / 16, pitch16 = ((w + 31) / 32 + 3) / 4 * 4 * 2;
   std::vector<uint16_t> pS((size_t)nframes * h * pitch16, 0), pC((size_t)nframes * h * pitch16, 0);

@@ -38,6 +38,8 @@ def lib():
         _lib.emu_stencil.argtypes = [_i, _vp, _ll, _ll, _i, _i, _i, _i, _i, C.c_uint, C.c_uint, _vp, _vp, _vp, _vp, _vp, _vp]
         _lib.emu_set_channels.restype = None
         _lib.emu_set_channels.argtypes = [_i]
+        _lib.emu_set_plane_stride.restype = None
+        _lib.emu_set_plane_stride.argtypes = [_ll]
         _lib.emu_hysteresis.restype = _i
         _lib.emu_hysteresis.argtypes = [_vp, _i, _i, _i, _vp, _vp]
         _lib.emu_band_create.restype = _vp
@@ -128,14 +130,17 @@ def hysteresis(map2, w, want_edges=True):
     return edges, bits
 
 
-def stencil_raw(buf, row0, w, h, lo=10, hi=40, impl=0, y0=0, h_glob=None, channels=3):
+def stencil_raw(buf, row0, w, h, lo=10, hi=40, impl=0, y0=0, h_glob=None, channels=3, plane_stride=0):
     """buf: 2-D uint8 array of padded rows (w * channels bytes used per row); the frame starts at row `row0`.  Returns
-    the 2-bit map or None if the implementation is not available in the emulator build."""
+    the 2-bit map or None if the implementation is not available in the emulator build.  plane_stride != 0: planar BGR8
+    (the G and R planes lie plane_stride and 2 * plane_stride bytes behind the B plane)."""
     h_glob = h if h_glob is None else h_glob
     map2 = np.zeros((h, (w + 15) // 16), np.uint32)
     lib().emu_set_channels(channels)
+    lib().emu_set_plane_stride(plane_stride)
     try:
         rc = lib().emu_stencil(impl, buf.ctypes.data + row0 * buf.strides[0], buf.strides[0], 0, w, h, y0, h_glob, 1, lo, hi, map2.ctypes.data, None, None, None, None, None)
     finally:
         lib().emu_set_channels(3)
+        lib().emu_set_plane_stride(0)
     return map2 if rc == 0 else None

@@ -47,6 +47,7 @@ def test_argument_errors_without_gpu():
     h = C.c_void_p()
     assert _lib.lib.b2c_create(C.byref(h), 0, 0, 10, 3, 1) == _lib.ERR_INVALID
     assert _lib.lib.b2c_create(C.byref(h), 0, 64, 48, 2, 1) == _lib.ERR_UNSUPPORTED   # channels must be 1 (GRAY8), 3 (BGR8) or 4 (BGRA8)
+    assert _lib.lib.b2c_create(C.byref(h), 0, 64, 48, 0x104, 1) == _lib.ERR_UNSUPPORTED   # only BGR8 has a planar form (0x103)
     assert _lib.lib.b2c_create(None, 0, 64, 48, 3, 1) == _lib.ERR_INVALID
     assert _lib.lib.b2c_run(None, None, 0, 5) == _lib.ERR_INVALID
     assert _lib.lib.b2c_get_low_threshold(None) == _lib.ERR_INVALID

@@ -200,3 +200,16 @@ def test_other_input_formats(kind, w, h, seed, ch):
         assert np.array_equal(e[k], r[k]), k
     m = E.stencil_raw(_padded(g, ch), 4, w, h, impl=126, channels=ch)
     assert m is not None and np.array_equal(m, O.thresh_to_map2(r["thresh"]))
+
+
+def test_planar_bgr_tile_kernel():
+    """Planar BGR8: the tile kernel reads the three planes; the marching kernel declines (returns None -> tile path)."""
+    w, h = 150, 70
+    f = synth.frame("scene", 12, w, h)
+    r = O.canny(f)
+    pitch = 160
+    buf = np.zeros((3 * h, pitch), np.uint8)
+    buf[:, :w] = f.transpose(2, 0, 1).reshape(3 * h, w)
+    m = E.stencil_raw(buf, 0, w, h, impl=1, plane_stride=pitch * h)
+    assert m is not None and np.array_equal(m, O.thresh_to_map2(r["thresh"]))
+    assert E.stencil_raw(buf, 0, w, h, impl=120, plane_stride=pitch * h) is None

@@ -249,3 +249,23 @@ def test_nv12_luma_plane():
         assert np.array_equal(c.edges(), r["edges"]) and np.array_equal(c.mono(), y)
     # and it is what the BGR path computes from the same picture (gray = (7B + 38G + 19R) >> 6, cannyEdgeD.cu:14-19)
     assert np.array_equal(r["edges"], O.canny(f)["edges"])
+
+
+def test_planar_bgr_input():
+    """Planar BGR8: three planes instead of interleaved pixels give the same result, through the
+    single-frame call with all accessors, a strided surface and the batch pipeline."""
+    w, h = 500, 281
+    f = synth.frame("scene", 33, w, h)
+    r = O.canny(f)
+    planes = np.ascontiguousarray(f.transpose(2, 0, 1))
+    with cb.CannyEdge(w, h, planar=True, max_batch=4) as c:
+        c.run(planes)
+        assert np.array_equal(c.edges(), r["edges"]) and np.array_equal(c.mono(), r["mono"]) and np.array_equal(c.nms(), r["nms"])
+        big = np.zeros((3 * h, 512), np.uint8)
+        big[:, :w] = planes.reshape(3 * h, w)
+        c.run(np.lib.stride_tricks.as_strided(big, (3, h, w), (512 * h, 512, 1)), cb.CannyStage.THRESH)
+        assert np.array_equal(c.thresh(), r["thresh"])
+        got = c.run_batch(np.stack([planes] * 5))
+        assert all(np.array_equal(got[i], r["edges"]) for i in range(5))
+    with pytest.raises(ValueError):
+        cb.CannyEdge(w, h, channels=1, planar=True)

@@ -8,8 +8,8 @@ w, h, n = 1920, 1080, 64
 host = cb.synth.batch("scene", n, w, h, distinct=8)
 d_in = torch.from_numpy(host.reshape(-1)).cuda()
 c = cb.CannyEdge(w, h, max_batch=n)
-for rb in (92, 272):
-  for extra in (0, 3000, 7000, 12000, 20000, 40000):
+for rb in (44, 92, 272):
+  for extra in (0, 1100, 2400, 3900, 5700, 7800, 12000, 20000):
     c.set_option("march_rb", rb); c.set_option("march_extra_smem", extra)
     for it in range(3): _lib.check(lib.b2c_stencil_device(c._h, d_in.data_ptr(), w * 3, w * 3 * h, n, None))
     c.sync(); t0 = time.perf_counter()
