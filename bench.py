@@ -85,22 +85,31 @@ class ClockSampler:
         except Exception:
             self.nv = None
 
-    def _loop(self):
+    NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake"}
+
+    def sample(self):
+        """One reading.  The timed loops call it themselves once all steps are issued and the GPU is still working through
+        them (a reading inside the timed region at no cost to it); the thread adds more on long runs."""
         nv = self.nv
-        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake"}
-        while not self._stop.is_set():
+        if not nv:
+            return
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev)
             except Exception:
-                pass
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+            for bit, name in self.NAMES.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _loop(self):
+        while not self._stop.is_set():
             time.sleep(0.02)   # (NVML queries take a driver lock: polling harder than this slows the launches of all ranks)
+            if not self._stop.is_set():
+                self.sample()
 
     def start(self):
         if self.nv and os.environ.get("B2C_NO_SAMPLER", "0") != "1":
@@ -383,9 +392,9 @@ def measure_giga(env, steps, warmup, W=16384, Hh=16384, want_edges=True):
     bc = bands.BandCanny(be, rank, world, dist if world > 1 else None)
     for _ in range(max(warmup, 3)):
         bc.run()
-    env.barrier()
     sampler = ClockSampler(env.local)
-    sampler.start()
+    sampler.start()   # (before the barrier: the thread's start-up and first NVML queries are not part of the timed region)
+    env.barrier()
     a, b = env.event(), env.event()
     l0 = be.launches
     a.record()
@@ -393,6 +402,7 @@ def measure_giga(env, steps, warmup, W=16384, Hh=16384, want_edges=True):
     for _ in range(steps):
         rounds = bc.run()
     b.record()
+    sampler.sample()   # all steps are issued, the GPU is still running them
     env.barrier()
     clocks = sampler.stop()
     launches = be.launches - l0
@@ -480,11 +490,11 @@ def run_ours(args, wl):
     for _ in range(warmup):
         stencil()
         hyst()
-    env.barrier()
     ev = [(env.event(), env.event(), env.event()) for _ in range(args.steps)]
     sampler = ClockSampler(local)
+    sampler.start()   # (before the barrier: the thread's start-up is not part of the timed region)
+    env.barrier()
     l0 = c.launches
-    sampler.start()
     for a, b, e in ev:
         a.record()
         stencil()
@@ -496,6 +506,7 @@ def run_ours(args, wl):
             hyst()
     ev_end = env.event()
     ev_end.record()
+    sampler.sample()   # all steps are issued, the GPU is still running them
     env.barrier()
     clocks = sampler.stop()
     launches = c.launches - l0
@@ -598,7 +609,8 @@ def run_ours(args, wl):
         if world == 1:
             lat = measure_latency_4k(env)
             line["latency_4k"] = lat
-        rec, _, _, _ = measure_giga(env, steps=max(3, min(args.steps, 10)), warmup=3)
+        # (at least 50 steps: a step is 0.25-0.9 ms, and one scheduling hiccup of a rank stalls all ranks of the band protocol)
+        rec, _, _, _ = measure_giga(env, steps=max(50, args.steps), warmup=5)
         if rank == 0:
             line["giga"] = rec
     if rank == 0:
@@ -609,6 +621,8 @@ def run_ours(args, wl):
 def run_giga(args, wl):
     """BASELINE configs[4] as its own bench line (strong scaling over the ranks)."""
     env = Env()
+    if os.environ.get("B2C_GIGA_H"):   # experiments only: a shorter image (bands as small as at 8 ranks on fewer GPUs)
+        wl = dict(wl, h=int(os.environ["B2C_GIGA_H"]))
     rec, total_ms, launches, clocks = measure_giga(env, args.steps, args.warmup, wl["w"], wl["h"])
     if env.rank == 0:
         peak, which = peaks()
