@@ -556,7 +556,12 @@ def run_ours(args, wl):
     same = bool(np.array_equal(out_host, dev_edges_host))
     same_bits = bool(np.array_equal(np.unpackbits(bits_host.view(np.uint8), axis=-1, bitorder="little")[:, :, :w] * 255, dev_edges_host))
     edge_frac = float((out_host == 255).mean())
-    ceiling = pcie_ceiling(env, px_per_chunk * 3, px_per_chunk) if rank == 0 or world > 1 else None
+    # every rank measures at the same time (barrier first): with N ranks on one box this is the per-GPU share of the
+    # host's PCIe complex under the same load pattern as the e2e run, not the link speed of one idle GPU
+    env.barrier()
+    ceiling = pcie_ceiling(env, px_per_chunk * 3, px_per_chunk)
+    if ceiling:
+        ceiling["ranks_copying_at_once"] = world
     lib.b2c_host_free(pin_in)
     lib.b2c_host_free(pin_out)
     stencil_impl = c.info("stencil_impl")
