@@ -76,16 +76,10 @@ struct B2cHystParams {
   int plane_pitch;           // u32 per row
   long long plane_frame_stride;
   int w, h, nframes;
-  uint8_t *edges;            // may be null (bit-plane consumers read S)
+  uint8_t *edges;            // u8 {0,255} map; may be null (bit-plane consumers read E)
   long long edges_pitch, edges_frame_stride;
-  int *flags;                // [0..2] round flags, [3] rounds used (out), [4] any-change-at-all (out)
-  int max_rounds;
-  int tile_rows;
-  int skip_init;             // 1 = S/C planes already built (row-band mode re-entry)
-  int skip_expand;           // 1 = do not write edges (row-band mode intermediate rounds)
+  int *flags;                // [3] on-device passes of the last run (= 1, out)
   int spread;                // tile kernel: 1 = deal the compacted work items round-robin to the warps, 0 = pack them
-  const int *skip;           // if non-null and *skip != 0 the resolve kernel does nothing (row-band P2P rounds after convergence)
-  const int *need;           // if non-null and *need == 0 the resolve kernel does nothing (this band was not seeded in this round)
   int *parent;               // union-find parents, one int per pixel of the padded plane (only weak pixels are used)
   long long parent_frame_stride;
 };

@@ -10,7 +10,7 @@
 //   every horizontal run of weak pixels inside a word is a node; a run that touches a strong pixel (3x3 dilation of S
 //   done on words) starts under node 0;
 //   unions with the weak W / NW / N / NE neighbours (atomicMin links the larger root under the smaller one, so 0 wins);
-//   resolve: a run is an edge iff find() == 0; S |= those bits; S expands to the u8 {0,255} map of the reference's PBO.
+//   resolve: a run is an edge iff find() == 0; E = S | those bits; E expands to the u8 {0,255} map of the reference's PBO.
 // Parent words that other CTAs may update are read with ld.global.cg (L2).
 #pragma once
 #include "b2c_device.cuh"
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(UT_THREADS) k_uf_tile(const B2cHystParams p, u
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wpr = (p.w + 31) >> 5;
   const int f = blockIdx.z, y0 = blockIdx.y * UT_ROWS, xw0 = blockIdx.x * UT_WORDS;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) { p.flags[3] = 1; p.flags[4] = 0; }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) p.flags[3] = 1;   // one on-device pass (b2c_last_timings [5])
   // ---- phase 0: S / C planes -> tile copies + compacted list of the words with weak pixels.  Two warps do it with
   // 128-bit loads (thread = 4 consecutive words of one tile row; rows are 16-byte aligned, words past the image are zero
   // padding), the other six go straight to the barrier: with one word per thread this phase alone was ~90 instructions
@@ -378,13 +378,6 @@ __device__ __forceinline__ bool uf_resolve_expand_word_sc(const B2cHystParams &p
   }
   return changed;
 }
-template <bool EXPAND, bool ONLY_CHANGED = false>
-__device__ __forceinline__ bool uf_resolve_expand_word(const B2cHystParams &p, int f, int y, int xw, int W32)
-{
-  const long long o = f * p.plane_frame_stride + (long long)y * p.plane_pitch + xw;
-  return uf_resolve_expand_word_sc<EXPAND, ONLY_CHANGED>(p, f, y, xw, W32, (ONLY_CHANGED ? p.E : p.S)[o], p.C[o]);
-}
-
 // One thread per plane word of TWO rows (both rows' loads in flight before either is looked at): block =
 // (blockDim.x words) x (2 * blockDim.y rows); grid: x = word blocks of a row, y = row blocks, z = frame.
 // LIST (row bands, one frame): the words with unresolved weak runs whose component reaches the band's first or last row
@@ -394,7 +387,6 @@ __device__ __forceinline__ bool uf_resolve_expand_word(const B2cHystParams &p, i
 template <bool EXPAND, bool LIST = false>
 __global__ void __launch_bounds__(UFK_THREADS) k_uf_resolve(const B2cHystParams p, int *bcount, uint2 *ulist = nullptr, int *ucount = nullptr, const int ucap = 0)
 {
-  if (p.skip && __ldcg(p.skip)) return;
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) bcount[blockIdx.z] = 0;   // the border list of this frame is consumed
   const int wpr = (p.w + 31) >> 5, W32 = p.plane_pitch * 32;
   const int xw = blockIdx.x * blockDim.x + threadIdx.x, y = 2 * (blockIdx.y * blockDim.y + threadIdx.y), f = blockIdx.z;
@@ -447,27 +439,4 @@ __global__ void __launch_bounds__(UFK_THREADS) k_uf_resolve_list(const B2cHystPa
   }
 }
 
-// expand: S plane -> u8 {0,255}; one thread per 16 pixels (one 128-bit store)
-__global__ void __launch_bounds__(UFK_THREADS) k_uf_expand(const B2cHystParams p)
-{
-  const int gpr = (p.w + 15) >> 4;
-  const long long total = (long long)p.nframes * p.h * gpr;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int row_ = (int)(i / gpr), g = (int)(i - (long long)row_ * gpr), f = row_ / p.h, y = row_ - f * p.h;
-    const uint32_t word = p.E[f * p.plane_frame_stride + (long long)y * p.plane_pitch + (g >> 1)];
-    const uint32_t bits = (word >> ((g & 1) * 16)) & 0xFFFFu;
-    uint8_t *out = p.edges + f * p.edges_frame_stride + (long long)y * p.edges_pitch + g * 16;
-    const int n = min(16, p.w - g * 16);
-    if (n == 16 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
-      uint4 v;
-      v.x = (((bits & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
-      v.y = ((((bits >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
-      v.z = ((((bits >> 8) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
-      v.w = ((((bits >> 12) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
-      *reinterpret_cast<uint4 *>(out) = v;
-    } else {
-      for (int k = 0; k < n; ++k) out[k] = ((bits >> k) & 1u) ? 255 : 0;
-    }
-  }
-}
 }// namespace b2c
