@@ -53,7 +53,7 @@ struct b2c_ctx {
   int march_rb = 0;           // rows per band of the marching kernel, 0 = automatic
   int march_ctas_per_sm = 0;  // resident CTAs per SM of the marching kernel (occupancy query at creation)
   int march_extra_smem = 0;   // profiling knob: extra dynamic shared memory per CTA (lowers the occupancy)
-  int uf_spread = 1;
+  int uf_spread = 0;   // tile kernel: warps the compacted work items are dealt to (1, 2, 4, 8); 0 = by batch size
 
   // geometry
   int map_pitch = 0;      // u32 per row of the 2-bit map
@@ -315,7 +315,8 @@ void fill_hyst_params(b2c_ctx *c, B2cHystParams &p, int n, uint8_t *edges, size_
   p.flags = c->d_flags;
   p.parent_frame_stride = (long long)c->rows_alloc * c->plane_pitch * 32;
   p.parent = c->d_parent + frame0 * p.parent_frame_stride;
-  p.spread = c->uf_spread;
+  // measured (tools/hyst_phases.py): one frame 17 us with 8 warps vs 19 with 4 (latency), 64 frames 93 us with 4 vs 97 with 8 (issue slots)
+  p.spread = c->uf_spread ? c->uf_spread : (n >= 8 ? 4 : 8);
 }
 
 // Union-find hysteresis of n frames from the planes the stencil wrote: three ordinary launches (tile, border,
@@ -1414,7 +1415,8 @@ int b2c_set_option(b2c_handle c, const char *name, int value)
     return B2C_OK;
   }
   if (!strcmp(name, "uf_spread")) {
-    c->uf_spread = value != 0;
+    if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return B2C_ERR_INVALID;
+    c->uf_spread = value;
     return B2C_OK;
   }
   if (!strcmp(name, "hyst_phase_timing")) {

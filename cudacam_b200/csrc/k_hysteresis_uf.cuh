@@ -213,10 +213,12 @@ __global__ void __launch_bounds__(UT_THREADS) k_uf_tile(const B2cHystParams p, u
   const int nitems = WC[UT_THREADS / 32];
   // ---- the remaining phases run on the compacted list: thread k takes the k-th word that holds weak pixels, so the
   // divergent per-run loops fill whole warps instead of a few lanes of every warp
-  // Items are dealt round-robin to the 8 warps (item = lane * 8 + warp), not packed into warp 0: the per-run loops
-  // are dependent chains of shared-memory atomics, so eight warps with a few busy lanes each finish sooner than one
-  // full warp while the other seven wait at the barrier (p.spread == 0 keeps the packed order for comparison).
-  const int item = p.spread ? lane * (UT_THREADS / 32) + warp : tid;
+  // Items are dealt round-robin to W warps, not packed into warp 0: the per-run loops are dependent chains of
+  // shared-memory atomics, so several warps with a few busy lanes each finish sooner than one full warp while the others
+  // wait at the barrier -- but every warp that takes part issues the whole divergent code: W = 8 is fastest for one frame
+  // (latency), W = 4 for big batches (issue slots).
+  // p.spread = W in {1, 2, 4, 8}: consecutive items are dealt to W warps (W = 1: packed, item = tid)
+  const int W = p.spread, item = (warp / W) * (32 * W) + lane * W + (warp % W);
   const bool act = item < nitems;
   const int t = act ? IT[item] : 0, ly = t >> 3, lw = t & 7, y = y0 + ly, xw = xw0 + lw;
   const uint32_t wd = act ? LW[t] : 0u;

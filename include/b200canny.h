@@ -197,7 +197,8 @@ B2C_API int b2c_bind_host_to_device(int device);
 /* kernels launched by this handle since creation (bench.py reports it as gpu_launches) */
 B2C_API long long b2c_launch_count(b2c_handle h);
 /* options: "stencil_impl" 0 = marching kernel (default), 1 = staged tile kernel (the all-stages path of the
- * accessors); "march_rb" rows per band of the marching kernel (0 = automatic); "hyst_phase_timing"; "uf_spread";
+ * accessors); "march_rb" rows per band of the marching kernel (0 = automatic); "hyst_phase_timing"; "uf_spread" (warps per tile the
+ * hysteresis work items are dealt to: 1, 2, 4, 8; 0 = chosen by batch size);
  * "seam_force_global" (tests: the large-seam code paths of the seam kernels) */
 B2C_API int b2c_set_option(b2c_handle h, const char *name, int value);
 /* read-only facts: "sm_count", "stencil_impl", "march_ctas_per_sm", "march_band_rows", "in_row_stride",

@@ -24,9 +24,11 @@ static void fill_gk(float gk[25])
 
 static int g_emu_channels = 3;
 static long long g_emu_plane_stride = 0;
+static int g_emu_spread = 8;
 extern "C" {
 __attribute__((visibility("default"))) void emu_set_channels(int ch) { g_emu_channels = ch; }
 __attribute__((visibility("default"))) void emu_set_plane_stride(long long s) { g_emu_plane_stride = s; }   // planar BGR8 (tile kernel)
+__attribute__((visibility("default"))) void emu_set_spread(int w) { g_emu_spread = w; }   // k_uf_tile: warps the work items are dealt to
 // impl: 1 = tile kernel (EMIT when any stage pointer is given), 100 + rb = marching kernel with rb rows per band
 __attribute__((visibility("default"))) int emu_stencil(int impl, const uint8_t *bgr, long long row_stride, long long frame_stride, int w, int h, int y0, int h_glob, int nframes,
                                                        unsigned lo, unsigned hi, uint32_t *map2, uint8_t *mono, uint8_t *blur, float *grad, uint8_t *nms, uint8_t *thresh)
@@ -122,7 +124,7 @@ struct EmuPlanes {
     p.S = S.data() + pitch; p.C = C.data() + pitch; p.E = E.data() + pitch; p.plane_pitch = pitch; p.plane_frame_stride = fs;
     p.w = w; p.h = h; p.nframes = n;
     p.edges = edges; p.edges_pitch = w; p.edges_frame_stride = (long long)w * h;
-    p.flags = flags; p.spread = 1;
+    p.flags = flags; p.spread = g_emu_spread;
     p.parent = parent.data(); p.parent_frame_stride = (long long)h * pitch * 32;
     return p;
   }

@@ -38,6 +38,8 @@ def lib():
         _lib.emu_stencil.argtypes = [_i, _vp, _ll, _ll, _i, _i, _i, _i, _i, C.c_uint, C.c_uint, _vp, _vp, _vp, _vp, _vp, _vp]
         _lib.emu_set_channels.restype = None
         _lib.emu_set_channels.argtypes = [_i]
+        _lib.emu_set_spread.restype = None
+        _lib.emu_set_spread.argtypes = [_i]
         _lib.emu_set_plane_stride.restype = None
         _lib.emu_set_plane_stride.argtypes = [_ll]
         _lib.emu_hysteresis.restype = _i
@@ -117,15 +119,20 @@ class Band:
         return out
 
 
-def hysteresis(map2, w, want_edges=True):
-    """(n, h, gpr) or (h, gpr) 2-bit maps -> (u8 edge maps or None, edge bit planes)."""
+def hysteresis(map2, w, want_edges=True, spread=8):
+    """(n, h, gpr) or (h, gpr) 2-bit maps -> (u8 edge maps or None, edge bit planes).  spread: warps per tile the work
+    items of k_uf_tile are dealt to (the product picks 8 for small batches, 4 for big ones)."""
     m = np.ascontiguousarray(map2, np.uint32)
     if m.ndim == 2:
         m = m[None]
     n, h, _ = m.shape
     edges = np.zeros((n, h, w), np.uint8) if want_edges else None
     bits = np.zeros((n, h, (w + 31) // 32), np.uint32)
-    rc = lib().emu_hysteresis(m.ctypes.data, w, h, n, None if edges is None else edges.ctypes.data, bits.ctypes.data)
+    lib().emu_set_spread(spread)
+    try:
+        rc = lib().emu_hysteresis(m.ctypes.data, w, h, n, None if edges is None else edges.ctypes.data, bits.ctypes.data)
+    finally:
+        lib().emu_set_spread(8)
     assert rc == 0
     return edges, bits
 

@@ -59,6 +59,16 @@ def test_hysteresis_kernel(kind, w, h, seed):
     assert none is None and np.array_equal(bits2, bits)
 
 
+@pytest.mark.parametrize("spread", [1, 2, 4])
+def test_hysteresis_item_order_variants(spread):
+    """k_uf_tile deals its work items to 1, 2, 4 or 8 warps (8 is what every other test runs): same result."""
+    rng = np.random.default_rng(11)
+    t = np.where(rng.random((70, 530)) < 0.35, 128, 0).astype(np.uint8)
+    t[rng.random(t.shape) < 0.002] = 255
+    edges, _ = E.hysteresis(O.thresh_to_map2(t), 530, spread=spread)
+    assert np.array_equal(edges[0], O.hysteresis(t))
+
+
 @pytest.mark.parametrize("dens", [0.1, 0.3, 0.5])
 def test_hysteresis_unionfind_random_maps(dens):
     rng = np.random.default_rng(int(dens * 10))

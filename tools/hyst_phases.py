@@ -6,12 +6,12 @@ import numpy as np, torch
 import cudacam_b200 as cb
 from cudacam_b200 import _lib
 lib = _lib.lib
-for (w, h, n) in [(3840, 2160, 1), (1920, 1080, 64), (1920, 1080, 8), (1920, 1080, 1), (16384, 2048, 1)]:
+for (w, h, n) in [(1920, 1080, 64), (1920, 1080, 8), (1920, 1080, 1)]:
     host = cb.synth.batch("scene", n, w, h, distinct=min(n, 16))
     d_in = torch.from_numpy(host.reshape(-1)).cuda()
     c = cb.CannyEdge(w, h, max_batch=max(n, 2))
     c.set_option("hyst_phase_timing", 1)
-    for spread in (1, 0):
+    for spread in (8, 4, 2, 1):
         c.set_option("uf_spread", spread)
         acc = np.zeros(3)
         for it in range(8):
