@@ -387,8 +387,8 @@ def measure_giga(env, steps, warmup, W=16384, Hh=16384, want_edges=True):
     be = bands.CudaBandBackend(W, rows, y0, Hh, device=env.local)
     be.load(band_host)
     p2p = world > 1 and os.environ.get("B2C_BAND_NCCL", "0") != "1"
-    if p2p:
-        be.enable_p2p(dist, rank, world)   # cross-band exchange on the devices (NVLink peer stores); B2C_BAND_NCCL=1 = NCCL
+    if p2p:   # cross-band exchange on the devices (NVLink peer stores); B2C_BAND_NCCL=1, or no CUDA IPC on this box: NCCL
+        p2p = be.enable_p2p(dist, rank, world)
     bc = bands.BandCanny(be, rank, world, dist if world > 1 else None)
     for _ in range(max(warmup, 3)):
         bc.run()
@@ -442,7 +442,7 @@ def measure_giga(env, steps, warmup, W=16384, Hh=16384, want_edges=True):
         rec = {"workload": WORKLOADS["giga"]["desc"], "width": W, "height": Hh, "bands": world, "band_rows_rank0": rows, "scaling": "strong",
                "ms_per_step": total_ms / steps, "value": px * steps / (total_ms * 1e-3) / 1e6, "unit": UNIT, "steps": steps,
                "global_hysteresis_exchanges": rounds, "phase_us_rank0": phases,
-               "protocol": ("peer-memory stores over NVLink + device-side seam solve" if p2p else "NCCL send/recv" if world > 1 else "single band"),
+               "protocol": ("peer-memory stores over NVLink + device-side seam solve" if p2p else "NCCL send/recv of the halo rows + all-gather of the seam records" if world > 1 else "single band"),
                "e2e_value": px * e2e_steps / e2e_s / 1e6, "edge_pixel_fraction_rank0": float((edges == 255).mean()),
                "sha256_edges": digest, "sha256_oracle_golden": golden, "equals_oracle_golden": (digest == golden) if (digest and golden) else None,
                "hbm_frac_whole_step": px * 4.0 / (total_ms / steps * 1e-3) / 1e9 / world / peaks()[0]}

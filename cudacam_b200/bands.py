@@ -116,15 +116,28 @@ class CudaBandBackend:
 
     # -- cross-band hysteresis and input halo: peer memory -------------------------------------------------------
     def enable_p2p(self, dist, rank, world, group=None):
-        """Maps the other ranks' mailboxes and input buffers (CUDA IPC).  Ranks must be on one box."""
+        """Maps the other ranks' mailboxes and input buffers (CUDA IPC).  Ranks must be on one box.  Collective: every
+        rank gets the same answer -- True, or False if ANY rank could not export or map (no CUDA IPC in this container,
+        no peer access ...); the band then keeps the collective transport."""
+        torch = self.torch
+        dev = f"cuda:{self.device}"
+
+        def all_ok(ok):
+            t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            return bool(t.item())
+
         h = (C.c_ubyte * 144)()
-        _lib.check(_lib.lib.b2c_band_p2p_export(self._h, h), self._h, "b2c_band_p2p_export")
-        mine = self.torch.tensor(list(h), dtype=self.torch.uint8, device=f"cuda:{self.device}")
-        allh = self.torch.empty(144 * world, dtype=self.torch.uint8, device=mine.device)
+        ok = _lib.lib.b2c_band_p2p_export(self._h, h) == 0
+        mine = torch.tensor(list(h), dtype=torch.uint8, device=dev)
+        allh = torch.empty(144 * world, dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(allh, mine, group=group)
+        if not all_ok(ok):
+            return False
         buf = bytes(allh.cpu().tolist())
-        _lib.check(_lib.lib.b2c_band_p2p_open(self._h, buf, world, rank), self._h, "b2c_band_p2p_open")
-        self.p2p = True
+        ok = _lib.lib.b2c_band_p2p_open(self._h, buf, world, rank) == 0
+        self.p2p = all_ok(ok)
+        return self.p2p
 
     def stencil_p2p(self, phase=0):
         """Halo exchange over peer memory hidden behind the stencil: only the CTAs next to a seam wait for the rows.
