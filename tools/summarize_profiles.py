@@ -68,7 +68,8 @@ def kernel_summary(name, px=None):
     tmp = f"/tmp/{TAG}_{name}_src.csv"
     open(tmp, "w").write(src)
     if name == "stencil":
-        a = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_march_stages.py"), rep, str(px)], capture_output=True, text=True).stdout
+        # (by the FUNCTIONS of k_stencil_march.cuh: tools/ncu_march_stages.py keyed stages by line ranges that went stale)
+        a = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_function.py"), rep, str(px)], capture_output=True, text=True).stdout
     else:
         a = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_stage_split.py"), tmp] + ([str(px)] if px else []), capture_output=True, text=True).stdout
     b = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_source_summary.py"), tmp, "30"], capture_output=True, text=True).stdout
