@@ -223,3 +223,45 @@ def test_planar_bgr_tile_kernel():
     m = E.stencil_raw(buf, 0, w, h, impl=1, plane_stride=pitch * h)
     assert m is not None and np.array_equal(m, O.thresh_to_map2(r["thresh"]))
     assert E.stencil_raw(buf, 0, w, h, impl=120, plane_stride=pitch * h) is None
+
+
+def test_hysteresis_tile_corner_cases():
+    """Structured cases around the corner of the 32-row x 256-pixel tiles of k_uf_tile (y = 32, x = 256):
+    contacts with promoted pixels of a neighbour tile straight and diagonally across the corner, a chain through four
+    tiles seeded in the last one, closed blobs, open components that die, the image's last row and column."""
+    w, h = 540, 70
+    t = np.zeros((h, w), np.uint8)
+    # (1) promoted run in tile (0,0) ends at (31,255); a weak pixel at (32,256) in tile (1,1) touches it only diagonally
+    t[31, 250:256] = 128
+    t[31, 250] = 255
+    t[32, 256] = 128
+    t[33, 257] = 128
+    # (2) a closed blob inside tile (0,1) (dead) and one with a strong pixel (promoted)
+    t[10:13, 300:303] = 128
+    t[20:23, 300:303] = 128
+    t[21, 301] = 255
+    # (3) chain through tiles (1,0) -> (1,1) -> (0,1) -> ... seeded at its far end in tile (0,1)
+    t[40, 200:300] = 128          # crosses x = 256 in the tile row below
+    t[33:41, 299] = 128           # up towards the tile border row 32
+    t[28:33, 298] = 128           # across y = 32, shifted by one column (diagonal contact)
+    t[28, 298:330] = 128
+    t[28, 330] = 255
+    # (4) an open component that reaches two tiles but no strong pixel: dies
+    t[50, 240:270] = 128
+    # (5) last row / last column
+    t[h - 1, 400:430] = 128
+    t[h - 1, 400] = 255
+    t[60:h, w - 1] = 128
+    t[60, w - 1] = 255
+    t[5:9, w - 1] = 128            # no seed: dies
+    want = O.hysteresis(t)
+    assert want[32, 256] == 255 and want[33, 257] == 255 and want[11, 301] == 0 and want[21, 300] == 255
+    assert want[40, 200] == 255 and want[50, 250] == 0 and want[h - 1, 429] == 255 and want[h - 1, w - 1] == 255 and want[6, w - 1] == 0
+    for spread in (8, 4):
+        edges, bits = E.hysteresis(O.thresh_to_map2(t), w, spread=spread)
+        assert np.array_equal(edges[0], want)
+        assert np.array_equal(bits[0], O.edges_to_bits(want))
+    # the transposed picture: the same contacts across the other kind of tile border
+    tt = np.ascontiguousarray(t.T)
+    edges, _ = E.hysteresis(O.thresh_to_map2(tt), h)
+    assert np.array_equal(edges[0], O.hysteresis(tt))
