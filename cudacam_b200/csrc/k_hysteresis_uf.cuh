@@ -364,15 +364,20 @@ __device__ __forceinline__ bool uf_resolve_expand_word_sc(const B2cHystParams &p
     uint8_t *out = p.edges + f * p.edges_frame_stride + (long long)y * p.edges_pitch + xw * 32;
     const int n = min(32, p.w - xw * 32);
     if (n == 32 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+      uint32_t v[8];   // 4 pixels per word: bit k -> byte k = 0 / 255
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const uint32_t bits = (s >> (16 * hh)) & 0xFFFFu;
-        uint4 v;
-        v.x = (((bits & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
-        v.y = ((((bits >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
-        v.z = ((((bits >> 8) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
-        v.w = ((((bits >> 12) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
-        reinterpret_cast<uint4 *>(out)[hh] = v;
+      for (int k = 0; k < 8; ++k) v[k] = ((((s >> (4 * k)) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+#ifndef B2C_EMU
+      if ((reinterpret_cast<uintptr_t>(out) & 31) == 0) {
+        // one 256-bit store per word (sm_100 STG.256): a lane writes its whole 32-byte sector at once; as two 128-bit
+        // stores every store instruction of a warp touched 32 half sectors (twice the L1 store transactions)
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                     : "memory");
+      } else
+#endif
+      {
+        reinterpret_cast<uint4 *>(out)[0] = make_uint4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<uint4 *>(out)[1] = make_uint4(v[4], v[5], v[6], v[7]);
       }
     } else {
       for (int k = 0; k < n; ++k) out[k] = ((s >> k) & 1u) ? 255 : 0;
