@@ -589,7 +589,7 @@ def run_ours(args, wl):
                        "l2_policy": "inputs (%.0f MB/launch/GPU) larger than the 126 MB L2, no flush" % (px_per_chunk * 3 / 1e6) if px_per_chunk * 3 > 130e6 else "input smaller than L2: latency workload, L2-warm",
                        "parallelism": f"frame-parallel x{world}, no collective", "stencil_impl": stencil_impl,
                        "e2e_equals_device_path": same, "e2e_bits_equal_device_path": same_bits, "edge_pixel_fraction": edge_frac},
-            "roofline": {"bound": "hbm", "kernel": "fused stencil (BGR8 -> 2-bit weak/strong map)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "kernel": "fused stencil k_stencil_march (BGR8 -> strong and weak|strong bit planes)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": which, "algorithmic_bytes_per_launch": px_per_chunk * STENCIL_BYTES_PER_PX,
                          "kernel_ms": k_ms, "hysteresis_ms": statistics.mean(hyst_ms), "stencil_share_of_step": sum(stencil_ms) / (sum(stencil_ms) + sum(hyst_ms))},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": px_per_step * 3, "d2h_bytes_per_step": px_per_step, "steps": e2e_steps,

@@ -89,7 +89,7 @@ class CannyEdge:
         return bool(lib.b2c_is_profiling_enabled(self._h))
 
     def lastTimings(self):
-        """dict of ms: upload, stencil, hysteresis, output, total (+ hysteresis rounds)."""
+        """dict of ms: upload, stencil, hysteresis, output, total; rounds = on-device hysteresis passes (always 1)."""
         v = (C.c_float * 6)()
         check(lib.b2c_last_timings(self._h, v, 6), self._h, "b2c_last_timings")
         return dict(upload=v[0], stencil=v[1], hysteresis=v[2], output=v[3], total=v[4], rounds=int(v[5]))

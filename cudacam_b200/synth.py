@@ -35,7 +35,8 @@ def batch(kind, n, w, h, stream=0, distinct=None):
 _GIGA_TILE = 4096
 _GIGA_PITCH = 3960   # mosaic pitch: NOT a divisor of the band heights (16384 / 2, 4, 8), so that the hard tile-to-tile
                      # edges of the mosaic do not lie exactly on the band seams (a picture-wide edge ON a seam makes
-                     # every weak chain along it cross the seam again and again: 25 global rounds instead of 3)
+                     # every weak chain along it cross the seam again and again -- the round-based protocol of round 1 needed
+                     # 25 global rounds there instead of 3; the seam-graph solve does not care, the picture is kept for comparability)
 
 
 def giga_rows(y0, y1, w=16384, h=16384):

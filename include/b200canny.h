@@ -79,7 +79,7 @@ B2C_API int b2c_get_high_threshold(b2c_handle h);
 /* ---- profiling toggle: enableKernelProfiling / isKernelProfilingEnabled (cannyEdgeH.hpp:31-32).
  * Timings are recorded with events and only read back by b2c_last_timings (no sync in the hot path,
  * unlike cannyEdgeH.cu:415-430).  ms[0]=upload, [1]=fused stencil, [2]=hysteresis, [3]=output, [4]=total,
- * [5]=0 (was: hysteresis rounds; the union-find needs none). */
+ * [5] = on-device hysteresis passes of that run (1: the union-find needs no rounds; the reference needs 16-30 launches). */
 B2C_API int b2c_enable_profiling(b2c_handle h, int on);
 B2C_API int b2c_is_profiling_enabled(b2c_handle h);
 B2C_API int b2c_last_timings(b2c_handle h, float *ms, int n);
